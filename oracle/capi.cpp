@@ -1,0 +1,132 @@
+// ORACLE - test infrastructure only.  Flat C entry points for ctypes (oracle/oracle.py).
+#include <cstring>
+#include <thread>
+
+#include "icp.hpp"
+#include "smallmat.hpp"
+
+using namespace wo;
+
+extern "C" {
+
+void *wo_kdtree_create(const float *xyzw, size_t n) { return new KdTree(xyzw, n, 4); }
+void wo_kdtree_destroy(void *t) { delete static_cast<KdTree *>(t); }
+
+void wo_kdtree_nn1(void *t, const float *q, size_t nq, int *idx, float *d2, int nthreads) {
+    const KdTree &tree = *static_cast<KdTree *>(t);
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) tree.nn1(q + 4 * i, idx + i, d2 + i);
+    };
+    if (nthreads <= 1) {
+        work(0, nq);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t chunk = (nq + nthreads - 1) / nthreads;
+    for (int k = 0; k < nthreads; ++k) {
+        const size_t lo = k * chunk, hi = std::min(nq, lo + chunk);
+        if (lo < hi) th.emplace_back(work, lo, hi);
+    }
+    for (auto &x : th) x.join();
+}
+
+// k-NN for nq queries; idx/d2 are nq*k, padded with -1 / inf
+void wo_kdtree_knn(void *t, const float *q, size_t nq, int k, int *idx, float *d2) {
+    const KdTree &tree = *static_cast<KdTree *>(t);
+    for (size_t i = 0; i < nq; ++i) {
+        const int found = tree.knn(q + 4 * i, k, idx + i * k, d2 + i * k);
+        for (int j = found; j < k; ++j) {
+            idx[i * k + j] = -1;
+            d2[i * k + j] = std::numeric_limits<float>::infinity();
+        }
+    }
+}
+
+// O(n*m) reference for the reference: lowest index among exact fp32 ties
+void wo_brute_nn1(const float *tgt, size_t nt, const float *q, size_t nq, int *idx, float *d2) {
+    for (size_t i = 0; i < nq; ++i) {
+        float best = std::numeric_limits<float>::infinity();
+        int bi = -1;
+        for (size_t j = 0; j < nt; ++j) {
+            const float *p = tgt + 4 * j;
+            if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
+            const float d = l2_simple(q + 4 * i, p);
+            if (d < best) {
+                best = d;
+                bi = (int) j;
+            }
+        }
+        idx[i] = bi;
+        d2[i] = best;
+    }
+}
+
+struct wo_icp_params_c {
+    double max_corr;
+    int max_iter;
+    double t_eps;
+    double fit_eps;
+    int estimator;
+    int sum_mode;
+};
+
+void *wo_icp_run(const float *src, size_t n_src, const float *tgt, size_t n_tgt, const float *normals,
+                 const wo_icp_params_c *p, void *prebuilt_tree, int nn_threads) {
+    IcpParams prm;
+    prm.max_corr = p->max_corr;
+    prm.max_iter = p->max_iter;
+    prm.t_eps = p->t_eps;
+    prm.fit_eps = p->fit_eps;
+    prm.estimator = p->estimator;
+    prm.sum_mode = p->sum_mode;
+    IcpResult *r = new IcpResult();
+    icp_align(src, n_src, tgt, n_tgt, normals, prm, *r, static_cast<KdTree *>(prebuilt_tree), nn_threads);
+    return r;
+}
+
+void wo_icp_result_summary(void *h, float *T16, int *converged, int *iters, int *state, size_t *n_corr,
+                           size_t *n_trace, size_t *n_aligned) {
+    const IcpResult &r = *static_cast<IcpResult *>(h);
+    std::memcpy(T16, r.final_T, sizeof r.final_T);
+    *converged = r.converged;
+    *iters = r.iterations;
+    *state = r.state;
+    *n_corr = r.corr_query.size();
+    *n_trace = r.trace.size();
+    *n_aligned = r.aligned.size() / 4;
+}
+
+void wo_icp_result_corr(void *h, int *q, int *m, float *d2) {
+    const IcpResult &r = *static_cast<IcpResult *>(h);
+    std::memcpy(q, r.corr_query.data(), r.corr_query.size() * sizeof(int));
+    std::memcpy(m, r.corr_match.data(), r.corr_match.size() * sizeof(int));
+    std::memcpy(d2, r.corr_dist.data(), r.corr_dist.size() * sizeof(float));
+}
+
+void wo_icp_result_aligned(void *h, float *xyzw) {
+    const IcpResult &r = *static_cast<IcpResult *>(h);
+    std::memcpy(xyzw, r.aligned.data(), r.aligned.size() * sizeof(float));
+}
+
+void wo_icp_result_trace(void *h, double *mse, int *n_corr, float *T16s) {
+    const IcpResult &r = *static_cast<IcpResult *>(h);
+    for (size_t i = 0; i < r.trace.size(); ++i) {
+        mse[i] = r.trace[i].mse;
+        n_corr[i] = r.trace[i].n_corr;
+        std::memcpy(T16s + 16 * i, r.trace[i].T, 16 * sizeof(float));
+    }
+}
+
+void wo_icp_result_free(void *h) { delete static_cast<IcpResult *>(h); }
+
+void wo_fix_scales(const float *src, size_t n_src, const float *tgt, size_t n_tgt, double max_corr, int *k3) {
+    const FixScales s = fix_scales(src, n_src, tgt, n_tgt, max_corr);
+    k3[0] = s.k_lin;
+    k3[1] = s.k_quad;
+    k3[2] = s.k_d2;
+}
+
+void wo_rotation_from_sigma(const double *S9, double *R9) { rotation_from_sigma(S9, R9); }
+int wo_solve6(const double *A36, const double *b6, double *x6) { return solve_pp<6>(A36, b6, x6) ? 1 : 0; }
+
+}  // extern "C"

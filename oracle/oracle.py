@@ -1,0 +1,187 @@
+"""ORACLE - test infrastructure only.
+
+ctypes front end of oracle/_build/libwave_oracle.so (the CPU restatement of the PCL algorithms
+the reference's match() calls; see oracle/*.hpp for the reference file:line each piece follows).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package libwave_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+import subprocess
+
+import numpy as np
+
+_DIR = pathlib.Path(__file__).resolve().parent
+_SO = _DIR / "_build" / "libwave_oracle.so"
+
+EST_SVD, EST_POINT_TO_PLANE = 0, 1
+SUM_EXACT, SUM_PCL = 0, 1
+CONV_STATES = ("NOT_CONVERGED", "ITERATIONS", "TRANSFORM", "ABS_MSE", "REL_MSE", "NO_CORRESPONDENCES")
+
+
+def build(force: bool = False) -> pathlib.Path:
+    """Compile the oracle with g++ (make -C oracle).  Building the checker is not using it."""
+    srcs = list(_DIR.glob("*.cpp")) + list(_DIR.glob("*.hpp")) + [_DIR / "Makefile"]
+    stale = (not _SO.exists()) or any(s.stat().st_mtime > _SO.stat().st_mtime for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", str(_DIR)], check=True, capture_output=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _SO.exists():
+            build()
+        _lib = C.CDLL(str(_SO))
+        _declare(_lib)
+    return _lib
+
+
+class IcpParamsC(C.Structure):
+    _fields_ = [("max_corr", C.c_double), ("max_iter", C.c_int), ("t_eps", C.c_double),
+                ("fit_eps", C.c_double), ("estimator", C.c_int), ("sum_mode", C.c_int)]
+
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+_dp = C.POINTER(C.c_double)
+
+
+def _declare(L):
+    L.wo_kdtree_create.restype = C.c_void_p
+    L.wo_kdtree_create.argtypes = [_fp, C.c_size_t]
+    L.wo_kdtree_destroy.argtypes = [C.c_void_p]
+    L.wo_kdtree_nn1.argtypes = [C.c_void_p, _fp, C.c_size_t, _ip, _fp, C.c_int]
+    L.wo_kdtree_knn.argtypes = [C.c_void_p, _fp, C.c_size_t, C.c_int, _ip, _fp]
+    L.wo_brute_nn1.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, _ip, _fp]
+    L.wo_icp_run.restype = C.c_void_p
+    L.wo_icp_run.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, _fp, C.POINTER(IcpParamsC), C.c_void_p, C.c_int]
+    L.wo_icp_result_summary.argtypes = [C.c_void_p, _fp, _ip, _ip, _ip, C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.wo_icp_result_corr.argtypes = [C.c_void_p, _ip, _ip, _fp]
+    L.wo_icp_result_aligned.argtypes = [C.c_void_p, _fp]
+    L.wo_icp_result_trace.argtypes = [C.c_void_p, _dp, _ip, _fp]
+    L.wo_icp_result_free.argtypes = [C.c_void_p]
+    L.wo_fix_scales.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, C.c_double, _ip]
+    L.wo_rotation_from_sigma.argtypes = [_dp, _dp]
+    L.wo_solve6.argtypes = [_dp, _dp, _dp]
+    L.wo_solve6.restype = C.c_int
+
+
+def xyzw(pts) -> np.ndarray:
+    """(n,3) or (n,4) -> contiguous fp32 (n,4) with w = 1 (pcl::PointXYZ layout)."""
+    pts = np.asarray(pts, dtype=np.float32)
+    if pts.ndim == 2 and pts.shape[1] == 4:
+        return np.ascontiguousarray(pts)
+    out = np.ones((pts.shape[0], 4), dtype=np.float32)
+    out[:, :3] = pts
+    return out
+
+
+def _f(a):
+    return a.ctypes.data_as(_fp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class KdTree:
+    def __init__(self, target):
+        self.pts = xyzw(target)
+        self.h = lib().wo_kdtree_create(_f(self.pts), self.pts.shape[0])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().wo_kdtree_destroy(self.h)
+            self.h = None
+
+    def nn1(self, queries, nthreads: int = 1):
+        q = xyzw(queries)
+        idx = np.empty(q.shape[0], dtype=np.int32)
+        d2 = np.empty(q.shape[0], dtype=np.float32)
+        lib().wo_kdtree_nn1(self.h, _f(q), q.shape[0], _i(idx), _f(d2), nthreads)
+        return idx, d2
+
+    def knn(self, queries, k: int):
+        q = xyzw(queries)
+        idx = np.empty((q.shape[0], k), dtype=np.int32)
+        d2 = np.empty((q.shape[0], k), dtype=np.float32)
+        lib().wo_kdtree_knn(self.h, _f(q), q.shape[0], k, _i(idx), _f(d2))
+        return idx, d2
+
+
+def brute_nn1(target, queries):
+    t, q = xyzw(target), xyzw(queries)
+    idx = np.empty(q.shape[0], dtype=np.int32)
+    d2 = np.empty(q.shape[0], dtype=np.float32)
+    lib().wo_brute_nn1(_f(t), t.shape[0], _f(q), q.shape[0], _i(idx), _f(d2))
+    return idx, d2
+
+
+class IcpResult:
+    pass
+
+
+def icp_align(source, target, *, max_corr=3.0, max_iter=100, t_eps=1e-8, fit_eps=1e-2,
+              estimator=EST_SVD, sum_mode=SUM_EXACT, target_normals=None, tree: KdTree | None = None,
+              nn_threads: int = 1) -> IcpResult:
+    """pcl::IterativeClosestPoint::align restated (oracle/icp.cpp); defaults = icp.hpp:35-43."""
+    s, t = xyzw(source), xyzw(target)
+    nrm = xyzw(target_normals) if target_normals is not None else None
+    prm = IcpParamsC(max_corr, max_iter, t_eps, fit_eps, estimator, sum_mode)
+    L = lib()
+    h = L.wo_icp_run(_f(s), s.shape[0], _f(t), t.shape[0], _f(nrm) if nrm is not None else None,
+                     C.byref(prm), tree.h if tree is not None else None, nn_threads)
+    T = np.empty(16, dtype=np.float32)
+    conv, iters, state = C.c_int(), C.c_int(), C.c_int()
+    nc, nt, na = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    L.wo_icp_result_summary(h, _f(T), C.byref(conv), C.byref(iters), C.byref(state), C.byref(nc),
+                            C.byref(nt), C.byref(na))
+    r = IcpResult()
+    r.T = T.reshape(4, 4)
+    r.converged, r.iterations, r.state = bool(conv.value), iters.value, CONV_STATES[state.value]
+    r.corr_query = np.empty(nc.value, dtype=np.int32)
+    r.corr_match = np.empty(nc.value, dtype=np.int32)
+    r.corr_dist = np.empty(nc.value, dtype=np.float32)
+    L.wo_icp_result_corr(h, _i(r.corr_query), _i(r.corr_match), _f(r.corr_dist))
+    r.aligned = np.empty((na.value, 4), dtype=np.float32)
+    L.wo_icp_result_aligned(h, _f(r.aligned))
+    r.mse = np.empty(nt.value, dtype=np.float64)
+    r.n_corr = np.empty(nt.value, dtype=np.int32)
+    r.T_trace = np.empty((nt.value, 4, 4), dtype=np.float32)
+    L.wo_icp_result_trace(h, _d(r.mse), _i(r.n_corr), _f(r.T_trace))
+    L.wo_icp_result_free(h)
+    return r
+
+
+def fix_scales(source, target, max_corr):
+    s, t = xyzw(source), xyzw(target)
+    k = np.empty(3, dtype=np.int32)
+    lib().wo_fix_scales(_f(s), s.shape[0], _f(t), t.shape[0], max_corr, _i(k))
+    return tuple(int(v) for v in k)
+
+
+def rotation_from_sigma(S):
+    S = np.ascontiguousarray(S, dtype=np.float64).reshape(9)
+    R = np.empty(9, dtype=np.float64)
+    lib().wo_rotation_from_sigma(_d(S), _d(R))
+    return R.reshape(3, 3)
+
+
+def solve6(A, b):
+    A = np.ascontiguousarray(A, dtype=np.float64).reshape(36)
+    b = np.ascontiguousarray(b, dtype=np.float64).reshape(6)
+    x = np.empty(6, dtype=np.float64)
+    ok = lib().wo_solve6(_d(A), _d(b), _d(x))
+    return x if ok else None
