@@ -1,0 +1,149 @@
+/* wavecu.h - the C ABI of the B200 registration hot path (libwavecu.so).
+ *
+ * This is the drop-in boundary for wave_matching's ICPMatcher / GICPMatcher / NDTMatcher::match():
+ * plain pointers and sizes, no C++/torch types.  The C++ shim in include/wave/matching/*.hpp
+ * (same class names and semantics as the reference headers) and the Python ctypes mirror in
+ * libwave_b200/matching.py both sit on top of exactly these entry points.
+ *
+ * What each group replaces in the reference (paths relative to wave_matching/):
+ *   wavecu_icp_create/destroy      pcl::IterativeClosestPoint member + parameter plumbing,
+ *                                  include/wave/matching/icp.hpp:100, src/icp.cpp:32-51
+ *   wavecu_icp_set_source/target   ICPMatcher::setRef/setTarget + icp.setInputSource/Target,
+ *                                  src/icp.cpp:67-73,124-125
+ *   wavecu_icp_match               icp.align + hasConverged + getFinalTransformation,
+ *                                  src/icp.cpp:126-128 (and the per-level calls :95-101,:116-119)
+ *   wavecu_icp_correspondences     icp.correspondences_, src/icp.cpp:213,
+ *                                  src/icp_pcl_functions.cpp:191
+ *   wavecu_icp_aligned             the "final" cloud written by align(), icp.hpp:109
+ *   wavecu_icp_info                ICPMatcher::estimateLUM / estimateCensi / estimateLUMold,
+ *                                  src/icp_pcl_functions.cpp:51-289, src/icp.cpp:167-397
+ *   wavecu_nn_*                    pcl::KdTreeFLANN::setInputCloud / nearestKSearch(k=1),
+ *                                  src/icp_pcl_functions.cpp:67-80
+ *   wavecu_voxel_grid              pcl::VoxelGrid::filter, src/icp.cpp:81-90,106-113,
+ *                                  src/gicp.cpp:39-40,49-50
+ *
+ * Conventions: clouds are arrays of pcl::PointXYZ records = 4 floats (x, y, z, pad) = "xyzw";
+ * 4x4 transforms are row-major doubles; every function returns 0 on success and a negative
+ * wavecu_status on failure (wavecu_last_error() gives the text).  Non-convergence is not an
+ * error: it is reported through the `converged` out-flag, as match() returns false
+ * (src/icp.cpp:132).  There is no CPU fallback: without a CUDA device every call fails with
+ * WAVECU_ERR_CUDA.  A handle is bound to one device and one stream and must not be used from two
+ * host threads at once; distinct handles are independent (MultiMatcher gives each worker its own,
+ * impl/multi_matcher_impl.hpp:22).
+ */
+#ifndef WAVECU_H
+#define WAVECU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    WAVECU_OK = 0,
+    WAVECU_ERR_ARG = -1,
+    WAVECU_ERR_CUDA = -2,
+    WAVECU_ERR_STATE = -3,
+    WAVECU_ERR_NCCL = -4
+} wavecu_status;
+
+enum { WAVECU_EST_SVD = 0, WAVECU_EST_POINT_TO_PLANE = 1 };
+enum { WAVECU_INFO_LUM = 0, WAVECU_INFO_CENSI = 1, WAVECU_INFO_LUMOLD = 2 };
+/* pcl::registration::DefaultConvergenceCriteria::ConvergenceState */
+enum {
+    WAVECU_CONV_NOT_CONVERGED = 0,
+    WAVECU_CONV_ITERATIONS = 1,
+    WAVECU_CONV_TRANSFORM = 2,
+    WAVECU_CONV_ABS_MSE = 3,
+    WAVECU_CONV_REL_MSE = 4,
+    WAVECU_CONV_NO_CORRESPONDENCES = 5
+};
+
+/* Field-for-field mirror of wave::ICPMatcherParams (icp.hpp:30-65) plus the estimator switch. */
+typedef struct {
+    double max_corr;        /* icp.hpp:35, default 3 */
+    int max_iter;           /* icp.hpp:37, default 100 */
+    double t_eps;           /* icp.hpp:41, default 1e-8 */
+    double fit_eps;         /* icp.hpp:43, default 1e-2 */
+    double lidar_ang_covar; /* icp.hpp:46, default 7.78e-9 */
+    double lidar_lin_covar; /* icp.hpp:49, default 2.5e-4 */
+    int multiscale_steps;   /* icp.hpp:54, default 3 */
+    float res;              /* icp.hpp:59, default 0.1 */
+    int covar_estimator;    /* icp.hpp:60-64, default LUM */
+    int estimator;          /* WAVECU_EST_*; the reference is always SVD (icp.hpp:100) */
+} wavecu_icp_params;
+
+void wavecu_icp_default_params(wavecu_icp_params *p);
+
+typedef struct wavecu_icp wavecu_icp;
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to launch on, or NULL for a stream owned by the
+ * handle. */
+int wavecu_icp_create(const wavecu_icp_params *params, int device, void *stream, wavecu_icp **out);
+int wavecu_icp_destroy(wavecu_icp *h);
+int wavecu_icp_set_params(wavecu_icp *h, const wavecu_icp_params *params);
+
+/* Host clouds (borrowed for the call, copied to the device inside). */
+int wavecu_icp_set_source(wavecu_icp *h, const float *xyzw, size_t n);
+int wavecu_icp_set_target(wavecu_icp *h, const float *xyzw, size_t n);
+/* Unit normals of the target, same order and stride as the target (point-to-plane only). */
+int wavecu_icp_set_target_normals(wavecu_icp *h, const float *nxyzw, size_t n);
+/* Device-resident clouds (device pointers on the handle's device; copied device-to-device). */
+int wavecu_icp_set_source_device(wavecu_icp *h, const void *d_xyzw, size_t n);
+int wavecu_icp_set_target_device(wavecu_icp *h, const void *d_xyzw, size_t n);
+int wavecu_icp_set_target_normals_device(wavecu_icp *h, const void *d_nxyzw, size_t n);
+
+/* One pcl align(): (re)builds the target search structure if the target changed, iterates on
+ * the device, returns final_transformation_ (fp32 values widened to double, row major). */
+int wavecu_icp_align(wavecu_icp *h, double T_out[16], int *converged, int *iterations, int *state);
+/* ICPMatcher::match() (src/icp.cpp:75-133): branches on params.res / multiscale_steps, voxel
+ * filtering and level composition included. */
+int wavecu_icp_match(wavecu_icp *h, double T_out[16], int *converged, int *iterations);
+
+/* correspondences_ of the last align() in ascending source index; buffers need room for the
+ * source size; *n receives the count. */
+int wavecu_icp_correspondences(wavecu_icp *h, int *idx_query, int *idx_match, float *dist2, size_t *n);
+/* final_transformation_ applied to the (possibly down-sampled) source; *n receives its size.
+ * xyzw may be NULL to query the size only. */
+int wavecu_icp_aligned(wavecu_icp *h, float *xyzw, size_t *n);
+/* Per-iteration trace of the last align(): mse[i], n_corr[i], T_inc[16*i..] (fp32 incremental
+ * transform, row major).  Arrays need room for max_iter entries; *n receives the count kept. */
+int wavecu_icp_trace(wavecu_icp *h, double *mse, int *n_corr, float *T_inc, int *n);
+int wavecu_icp_info(wavecu_icp *h, int method, double info_out[36]);
+
+/* Timing and launch counters of the last align()/match(), measured with CUDA events on the
+ * handle's stream when profiling is enabled (adds one event pair per kernel). */
+typedef struct {
+    double build_ms;        /* search-structure build (sort + tree) */
+    double iterate_ms;      /* sum over iterations of the fused correspondence kernel */
+    double solve_ms;        /* sum of the estimator/convergence kernel */
+    double total_ms;        /* whole align()/match() on the stream */
+    long long iterate_launches;
+    long long kernel_launches; /* every kernel this library launched in the call */
+    long long pairs;        /* sum over iterations of source points queried */
+} wavecu_stats;
+int wavecu_icp_set_profiling(wavecu_icp *h, int enabled);
+int wavecu_icp_stats(wavecu_icp *h, wavecu_stats *out);
+
+/* Stand-alone exact 1-NN (the correspondence kernel without the estimator). */
+typedef struct wavecu_nn wavecu_nn;
+int wavecu_nn_create(int device, void *stream, wavecu_nn **out);
+int wavecu_nn_destroy(wavecu_nn *h);
+int wavecu_nn_set_target(wavecu_nn *h, const float *xyzw, size_t n);
+/* idx[i] = index of the nearest target point (lowest index among exact fp32 ties), -1 if none
+ * within max_dist (max_dist <= 0: unlimited); dist2[i] = fp32 squared distance. */
+int wavecu_nn_search(wavecu_nn *h, const float *q_xyzw, size_t nq, double max_dist, int *idx, float *dist2);
+/* Same on device-resident queries/outputs; elapsed_ms (may be NULL) receives the device time of
+ * `repeats` back-to-back searches measured with CUDA events on the handle's stream. */
+int wavecu_nn_search_device(wavecu_nn *h, const void *d_q_xyzw, size_t nq, double max_dist, void *d_idx,
+                            void *d_dist2, int repeats, float *elapsed_ms);
+
+const char *wavecu_last_error(void);
+int wavecu_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVECU_H */

@@ -1,0 +1,444 @@
+// Device side of one ICP iteration (pcl::IterativeClosestPoint::computeTransformation, SURVEY.md
+// Appendix A.3-A.5; reference call sites wave_matching/src/icp.cpp:95,116,126).
+//
+//   iterate_kernel  fuses, per source point: the in-place incremental fp32 transform of the working
+//                   cloud (A.3.2), the exact 1-NN correspondence search with the max-distance test
+//                   (A.3.1), and the estimator's reduction - {n, sum p, sum q, sum q p^T, sum d2}
+//                   for the SVD estimator (A.4) or the 21+6 entries of J^T J / J^T r for
+//                   point-to-plane (8(a) A7) - as exact 128-bit fixed-point sums (DESIGN.md
+//                   "Estimator arithmetic"): warp butterfly -> block -> a few 64-bit atomics.
+//   solve_kernel    one thread: sums -> Umeyama rotation (one-sided Jacobi, fp64, fixed order) or
+//                   6x6 solve, fp32 cast, final = T * final, DefaultConvergenceCriteria (A.5).
+#pragma once
+#include "common.cuh"
+#include "index.cuh"
+
+namespace wavecu {
+
+constexpr int kIterThreads = 128;
+constexpr int kQueriesPerThread = 4;
+constexpr int kIterWarps = kIterThreads / 32;
+
+struct IterArgs {
+    float4 *cur;                 // working source cloud, Morton order, w = original index
+    int n_src;
+    const Node *nodes;
+    const float4 *tgt;
+    const float4 *nrm;           // sorted target normals (point-to-plane) or nullptr
+    int P;
+    int *nn_pos;                 // sorted position of the match (-1: none) - warm start + gathers
+    int *nn_idx;                 // original target index of the match (-1: none)
+    float *nn_d2;
+    IcpState *st;
+    const MatchConsts *mc;
+    Acc128 *acc;                 // [kAccSlots][kMaxAcc]
+};
+
+template <int EST>
+struct EstTraits;
+template <>
+struct EstTraits<WAVECU_EST_SVD> {
+    static constexpr int NV = 16;  // 3 + 3 + 9 + 1 (count travels separately)
+};
+template <>
+struct EstTraits<WAVECU_EST_POINT_TO_PLANE> {
+    static constexpr int NV = 32;  // 21 + 6 + 1, padded
+};
+
+__device__ __forceinline__ long long shfl_xor_ll(long long v, int mask) {
+    int lo = (int) (unsigned long long) v, hi = (int) ((unsigned long long) v >> 32);
+    lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return (long long) (((unsigned long long) (unsigned) hi << 32) | (unsigned) lo);
+}
+
+// Transposing warp reduction of NV (16 or 32) 64-bit values: ~NV shuffles instead of 5 NV.
+// On return v[0] of lane L holds the warp total of value (L * NV) / 32.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_transpose(long long (&v)[NV], int lane) {
+    int bit = 16;
+#pragma unroll
+    for (int half = NV / 2; half >= 1; half >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const long long keep = upper ? v[half + i] : v[i];
+            const long long send = upper ? v[i] : v[half + i];
+            v[i] = keep + shfl_xor_ll(send, bit);
+        }
+        bit >>= 1;
+    }
+    for (; bit >= 1; bit >>= 1) v[0] += shfl_xor_ll(v[0], bit);
+}
+
+template <int EST>
+__global__ void __launch_bounds__(kIterThreads) iterate_kernel(IterArgs a) {
+    constexpr int NV = EstTraits<EST>::NV;
+    if (a.st->done) return;
+    __shared__ long long s_part[kIterWarps][NV + 1];
+
+    float T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = a.st->T_inc[i];
+    const float thr = a.mc->thr;
+    const double s_lin = a.mc->s_lin, s_quad = a.mc->s_quad, s_d2 = a.mc->s_d2, s_plane = a.mc->s_plane;
+
+    long long v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 0;
+    int count = 0;
+
+    const int base = blockIdx.x * (kIterThreads * kQueriesPerThread) + threadIdx.x;
+#pragma unroll 1
+    for (int r = 0; r < kQueriesPerThread; ++r) {
+        const int s = base + r * kIterThreads;
+        if (s >= a.n_src) break;
+        float4 c = a.cur[s];
+        if (!finite3(c.x, c.y, c.z)) {  // pads and non-finite source points take no part
+            a.nn_pos[s] = -1;
+            a.nn_idx[s] = -1;
+            a.nn_d2[s] = INFINITY;
+            continue;
+        }
+        const float x = xform_row(T + 0, c.x, c.y, c.z);
+        const float y = xform_row(T + 4, c.x, c.y, c.z);
+        const float z = xform_row(T + 8, c.x, c.y, c.z);
+        a.cur[s] = make_float4(x, y, z, c.w);
+
+        float best = thr;
+        int best_idx = 0x7fffffff, best_pos = -1;
+        const int warm = a.nn_pos[s];
+        if (warm >= 0) {
+            const float4 p = __ldg(a.tgt + warm);
+            const float d = l2_simple(x, y, z, p.x, p.y, p.z);
+            if (d <= best) {
+                best = d;
+                best_idx = __float_as_int(p.w);
+                best_pos = warm;
+            }
+        }
+        nn_search(x, y, z, a.nodes, a.tgt, a.P, best, best_idx, best_pos);
+        a.nn_pos[s] = best_pos;
+        a.nn_idx[s] = best_pos >= 0 ? best_idx : -1;
+        a.nn_d2[s] = best;
+        if (best_pos < 0) continue;
+
+        ++count;
+        const float4 q = __ldg(a.tgt + best_pos);
+        if (EST == WAVECU_EST_SVD) {
+            const double px = x, py = y, pz = z, qx = q.x, qy = q.y, qz = q.z;
+            v[0] += __double2ll_rn(px * s_lin);
+            v[1] += __double2ll_rn(py * s_lin);
+            v[2] += __double2ll_rn(pz * s_lin);
+            v[3] += __double2ll_rn(qx * s_lin);
+            v[4] += __double2ll_rn(qy * s_lin);
+            v[5] += __double2ll_rn(qz * s_lin);
+            v[6] += __double2ll_rn((qx * px) * s_quad);
+            v[7] += __double2ll_rn((qx * py) * s_quad);
+            v[8] += __double2ll_rn((qx * pz) * s_quad);
+            v[9] += __double2ll_rn((qy * px) * s_quad);
+            v[10] += __double2ll_rn((qy * py) * s_quad);
+            v[11] += __double2ll_rn((qy * pz) * s_quad);
+            v[12] += __double2ll_rn((qz * px) * s_quad);
+            v[13] += __double2ll_rn((qz * py) * s_quad);
+            v[14] += __double2ll_rn((qz * pz) * s_quad);
+            v[15] += __double2ll_rn((double) best * s_d2);
+        } else {
+            v[27] += __double2ll_rn((double) best * s_d2);
+            const float4 nn = __ldg(a.nrm + best_pos);
+            if (finite3(nn.x, nn.y, nn.z)) {
+                // TransformationEstimationPointToPlaneLLS: a, b, c, d evaluated in fp32
+                double J[6];
+                J[0] = __fsub_rn(__fmul_rn(nn.z, y), __fmul_rn(nn.y, z));
+                J[1] = __fsub_rn(__fmul_rn(nn.x, z), __fmul_rn(nn.z, x));
+                J[2] = __fsub_rn(__fmul_rn(nn.y, x), __fmul_rn(nn.x, y));
+                J[3] = nn.x;
+                J[4] = nn.y;
+                J[5] = nn.z;
+                float df = __fadd_rn(__fadd_rn(__fmul_rn(nn.x, q.x), __fmul_rn(nn.y, q.y)), __fmul_rn(nn.z, q.z));
+                df = __fsub_rn(df, __fmul_rn(nn.x, x));
+                df = __fsub_rn(df, __fmul_rn(nn.y, y));
+                df = __fsub_rn(df, __fmul_rn(nn.z, z));
+                const double d = df;
+                int u = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                    for (int j = i; j < 6; ++j) v[u++] += __double2ll_rn((J[i] * J[j]) * s_plane);
+                    v[21 + i] += __double2ll_rn((J[i] * d) * s_plane);
+                }
+            }
+        }
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    warp_reduce_transpose<NV>(v, lane);
+    count = __reduce_add_sync(0xffffffffu, count);
+    constexpr int kLanesPerValue = 32 / NV;
+    if ((lane % kLanesPerValue) == 0) s_part[warp][lane / kLanesPerValue] = v[0];
+    if (lane == 0) s_part[warp][NV] = count;
+    __syncthreads();
+    if (threadIdx.x <= NV) {
+        __int128 tot = 0;
+#pragma unroll
+        for (int w = 0; w < kIterWarps; ++w) tot += (__int128) s_part[w][threadIdx.x];
+        if (tot != 0) {
+            Acc128 *dst = a.acc + (blockIdx.x % kAccSlots) * kMaxAcc + threadIdx.x;
+            atomic_add128(dst, (unsigned long long) tot, (long long) (tot >> 64));
+        }
+    }
+}
+
+struct SolveArgs {
+    IcpState *st;
+    const MatchConsts *mc;
+    Acc128 *acc;
+    TraceRow *trace;
+    int max_iter;
+    double t_eps, fit_eps;
+};
+
+// Rotation maximising trace(R^T S): one-sided Jacobi on S, fixed pair order, <= 12 sweeps (stops
+// early only at an exact fixed point, which leaves the result unchanged).
+__device__ inline void rotation_from_sigma(const double S[9], double R[9]) {
+    double A[3][3], V[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            A[i][j] = S[3 * i + j];
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        bool changed = false;
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+            const int p = (pr == 2) ? 1 : 0, q = (pr == 0) ? 1 : 2;
+            const double alpha = (A[0][p] * A[0][p] + A[1][p] * A[1][p]) + A[2][p] * A[2][p];
+            const double beta = (A[0][q] * A[0][q] + A[1][q] * A[1][q]) + A[2][q] * A[2][q];
+            const double gamma = (A[0][p] * A[0][q] + A[1][p] * A[1][q]) + A[2][p] * A[2][q];
+            if (gamma == 0.0) continue;
+            const double zeta = (beta - alpha) / (2.0 * gamma);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + t * t);
+            const double s = c * t;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double ap = A[i][p], aq = A[i][q];
+                const double nap = c * ap - s * aq, naq = s * ap + c * aq;
+                const double vp = V[i][p], vq = V[i][q];
+                const double nvp = c * vp - s * vq, nvq = s * vp + c * vq;
+                changed |= (nap != ap) | (naq != aq) | (nvp != vp) | (nvq != vq);
+                A[i][p] = nap;
+                A[i][q] = naq;
+                V[i][p] = nvp;
+                V[i][q] = nvq;
+            }
+        }
+        if (!changed) break;
+    }
+    double nrm2[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) nrm2[j] = (A[0][j] * A[0][j] + A[1][j] * A[1][j]) + A[2][j] * A[2][j];
+    int i1 = 0;
+    if (nrm2[1] > nrm2[i1]) i1 = 1;
+    if (nrm2[2] > nrm2[i1]) i1 = 2;
+    int i2 = -1;
+    for (int j = 0; j < 3; ++j) {
+        if (j == i1) continue;
+        if (i2 < 0 || nrm2[j] > nrm2[i2]) i2 = j;
+    }
+    const double s1 = sqrt(nrm2[i1]), s2 = sqrt(nrm2[i2]);
+    if (!(s1 > 0.0) || !(s2 > 0.0)) {
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    double u1[3], u2[3], v1[3], v2[3], u3[3], v3[3];
+    for (int i = 0; i < 3; ++i) {
+        u1[i] = A[i][i1] / s1;
+        u2[i] = A[i][i2] / s2;
+        v1[i] = V[i][i1];
+        v2[i] = V[i][i2];
+    }
+    u3[0] = u1[1] * u2[2] - u1[2] * u2[1];
+    u3[1] = u1[2] * u2[0] - u1[0] * u2[2];
+    u3[2] = u1[0] * u2[1] - u1[1] * u2[0];
+    v3[0] = v1[1] * v2[2] - v1[2] * v2[1];
+    v3[1] = v1[2] * v2[0] - v1[0] * v2[2];
+    v3[2] = v1[0] * v2[1] - v1[1] * v2[0];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = (u1[i] * v1[j] + u2[i] * v2[j]) + u3[i] * v3[j];
+}
+
+// 6x6 Gaussian elimination with partial pivoting, fixed order; false if singular.
+__device__ inline bool solve6(const double A_in[36], const double b_in[6], double x[6]) {
+    double A[6][7];
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) A[i][j] = A_in[6 * i + j];
+        A[i][6] = b_in[i];
+    }
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        double best = fabs(A[c][c]);
+        for (int r = c + 1; r < 6; ++r)
+            if (fabs(A[r][c]) > best) {
+                best = fabs(A[r][c]);
+                piv = r;
+            }
+        if (best == 0.0 || !isfinite(best)) return false;
+        if (piv != c)
+            for (int j = 0; j <= 6; ++j) {
+                const double t = A[c][j];
+                A[c][j] = A[piv][j];
+                A[piv][j] = t;
+            }
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = A[r][c] / A[c][c];
+            for (int j = c; j <= 6; ++j) A[r][j] = A[r][j] - f * A[c][j];
+        }
+    }
+    for (int r = 5; r >= 0; --r) {
+        double s = A[r][6];
+        for (int j = r + 1; j < 6; ++j) s = s - A[r][j] * x[j];
+        x[r] = s / A[r][r];
+    }
+    return true;
+}
+
+template <int EST>
+__global__ void solve_kernel(SolveArgs a) {
+    constexpr int NV = EstTraits<EST>::NV;
+    if (threadIdx.x != 0 || a.st->done) return;
+    IcpState &st = *a.st;
+    const MatchConsts &mc = *a.mc;
+
+    __int128 tot[NV + 1];
+    for (int i = 0; i <= NV; ++i) {
+        __int128 t = 0;
+        for (int sl = 0; sl < kAccSlots; ++sl) {
+            Acc128 &c = a.acc[sl * kMaxAcc + i];
+            t += ((__int128) c.hi << 64) + (__int128) c.lo;
+            c.lo = 0;
+            c.hi = 0;
+        }
+        tot[i] = t;
+    }
+    auto val = [&](int i, int k) { return acc_to_double((unsigned long long) tot[i], (long long) (tot[i] >> 64), k); };
+    const long long n = (long long) tot[NV];
+    if (n < 3) {  // min_number_correspondences_
+        st.n_corr = (int) n;
+        st.converged = 0;
+        st.state = WAVECU_CONV_NO_CORRESPONDENCES;
+        st.done = 1;
+        return;
+    }
+    const double dn = (double) n;
+    float T[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    double mse;
+    if (EST == WAVECU_EST_SVD) {
+        double sp[3], sq[3], mp[3], mq[3], S[9], R[9];
+        for (int c = 0; c < 3; ++c) {
+            sp[c] = val(c, mc.k_lin);
+            sq[c] = val(3 + c, mc.k_lin);
+            mp[c] = sp[c] / dn;
+            mq[c] = sq[c] / dn;
+        }
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) S[3 * r + c] = (val(6 + 3 * r + c, mc.k_quad) - (sq[r] * sp[c]) / dn) / dn;
+        rotation_from_sigma(S, R);
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) T[4 * r + c] = (float) R[3 * r + c];
+            const double rr = (R[3 * r + 0] * mp[0] + R[3 * r + 1] * mp[1]) + R[3 * r + 2] * mp[2];
+            T[4 * r + 3] = (float) (mq[r] - rr);
+        }
+        mse = val(15, mc.k_d2) / dn;
+    } else {
+        double ATA[36], ATb[6], x[6];
+        const int k = mc.k_quad - 3;
+        int u = 0;
+        for (int r = 0; r < 6; ++r) {
+            for (int c = r; c < 6; ++c) {
+                ATA[6 * r + c] = ATA[6 * c + r] = val(u, k);
+                ++u;
+            }
+            ATb[r] = val(21 + r, k);
+        }
+        mse = val(27, mc.k_d2) / dn;
+        if (!solve6(ATA, ATb, x)) {
+            st.n_corr = (int) n;
+            st.converged = 0;
+            st.state = WAVECU_CONV_NO_CORRESPONDENCES;
+            st.done = 1;
+            return;
+        }
+        const double al = x[0], be = x[1], ga = x[2];
+        T[0] = (float) (cos(ga) * cos(be));
+        T[1] = (float) (-sin(ga) * cos(al) + cos(ga) * sin(be) * sin(al));
+        T[2] = (float) (sin(ga) * sin(al) + cos(ga) * sin(be) * cos(al));
+        T[4] = (float) (sin(ga) * cos(be));
+        T[5] = (float) (cos(ga) * cos(al) + sin(ga) * sin(be) * sin(al));
+        T[6] = (float) (-cos(ga) * sin(al) + sin(ga) * sin(be) * cos(al));
+        T[8] = (float) (-sin(be));
+        T[9] = (float) (cos(be) * sin(al));
+        T[10] = (float) (cos(be) * cos(al));
+        T[3] = (float) x[3];
+        T[7] = (float) x[4];
+        T[11] = (float) x[5];
+    }
+
+    // final_transformation_ = transformation_ * final_transformation_ (fp32, Eigen column order)
+    float F[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            float acc = __fmul_rn(T[4 * r + 0], st.T_final[c]);
+            acc = __fadd_rn(__fmul_rn(T[4 * r + 1], st.T_final[4 + c]), acc);
+            acc = __fadd_rn(__fmul_rn(T[4 * r + 2], st.T_final[8 + c]), acc);
+            acc = __fadd_rn(__fmul_rn(T[4 * r + 3], st.T_final[12 + c]), acc);
+            F[4 * r + c] = acc;
+        }
+    for (int i = 0; i < 16; ++i) {
+        st.T_final[i] = F[i];
+        st.T_inc[i] = T[i];
+    }
+    const int it = ++st.iter;
+    st.n_corr = (int) n;
+    if (a.trace) {
+        TraceRow &row = a.trace[it - 1];
+        row.mse = mse;
+        row.n_corr = (int) n;
+        for (int i = 0; i < 16; ++i) row.T[i] = T[i];
+    }
+
+    // DefaultConvergenceCriteria::hasConverged; cos_angle / translation_sqr are fp32 expressions
+    int conv = 0, state = WAVECU_CONV_NOT_CONVERGED;
+    if (it >= a.max_iter) {
+        conv = 1;
+        state = WAVECU_CONV_ITERATIONS;
+    } else {
+        const float tr = __fsub_rn(__fadd_rn(__fadd_rn(T[0], T[5]), T[10]), 1.0f);
+        const double cos_angle = 0.5 * (double) tr;
+        const float t2 = __fadd_rn(__fadd_rn(__fmul_rn(T[3], T[3]), __fmul_rn(T[7], T[7])), __fmul_rn(T[11], T[11]));
+        const double translation_sqr = (double) t2;
+        if (cos_angle >= 1.0 - a.t_eps && translation_sqr <= a.t_eps) {
+            conv = 1;
+            state = WAVECU_CONV_TRANSFORM;
+        } else if (fabs(mse - st.prev_mse) < 1e-12) {
+            conv = 1;
+            state = WAVECU_CONV_ABS_MSE;
+        } else if (fabs(mse - st.prev_mse) / st.prev_mse < a.fit_eps) {
+            conv = 1;
+            state = WAVECU_CONV_REL_MSE;
+        } else {
+            st.prev_mse = mse;
+        }
+    }
+    if (conv) {
+        st.converged = 1;
+        st.state = state;
+        st.done = 1;
+    }
+}
+
+}  // namespace wavecu
