@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the registration hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one ICPMatcher::match() (point-to-plane estimator, full resolution, reference
+default parameters) of a 1 M-point synthetic Velodyne-style scan against a 1 M-point scan of the
+same scene (BASELINE.json configs[1]; generator: libwave_b200/synth.py), search
+structure build included.  Metric: point-pairs/s = sum over ICP iterations of source points queried
+/ time.  N > 1: the batch-of-scans case - every rank matches its own scan pair (weak scaling), no
+data-path collective, one NCCL all-gather of the 4x4 results per step.
+
+`value`    inputs already resident in HBM, timed with CUDA events on the launch stream.
+`e2e`      the same match through the public host API from pinned host clouds (H2D copies and the
+           result read-back inside the timed region).
+`roofline` the fused correspondence kernel: algorithmic bytes per launch / mean launch time
+           (CUDA events around every launch, inside the timed region) against the measured HBM
+           copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` / --impl reference: the CPU oracle (restated PCL path; the real PCL cannot be built
+           here) on the host cores, MultiMatcher-style: one single-threaded
+           match per hardware thread, each capped at a few iterations (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_POINTS = 1_000_000
+CPU_SAMPLE_ITERS = 6          # iterations per CPU sample match (build included)
+METRIC = "point-pairs/s (1M-pt ICP)"
+UNIT = "point-pairs/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def make_workload(rank: int):
+    from libwave_b200 import synth
+    src, tgt, nrm = synth.scan_pair(N_POINTS, scan_id=None if rank == 0 else rank, return_normals=True)
+    return synth.to_xyzw(src), synth.to_xyzw(tgt), synth.to_xyzw(nrm)
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": "ICPMatcher point-to-plane, 1M-point synthetic Velodyne-style scan vs 1M-point scan of the "
+                    "same scene, res=-1 (full resolution), max_corr=3, max_iter=100, t_eps=1e-8, fit_eps=1e-2",
+        "n_source": N_POINTS, "n_target": N_POINTS, "estimator": "point_to_plane_lls",
+        "normals": "analytic surface normals from the generator, uploaded with the target",
+        "parallelism": f"batch-of-scans x{n_gpus} (one independent scan pair per GPU)",
+        "l2": "flushed between timed steps (256 MiB write); inside a step the clouds are re-read every ICP "
+              "iteration by design",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def finish(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 10:
+                continue
+            try:
+                sm.append(float(p[2]))
+                smax.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[6:10]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(src, tgt, nrm, threads: int):
+    """The oracle's PCL-faithful ICP on the host cores, MultiMatcher-style (one single-threaded match
+    per hardware thread, multi_matcher.hpp:32).  Returns (pairs_per_s, description, seconds)."""
+    from oracle import oracle as O
+    O.build()
+    O.lib()
+    done = [0] * threads
+
+    def work(k):
+        r = O.icp_align(src, tgt, estimator=O.EST_POINT_TO_PLANE, sum_mode=O.SUM_PCL, target_normals=nrm,
+                        max_iter=CPU_SAMPLE_ITERS, nn_threads=1)
+        done[k] = r.iterations * src.shape[0]
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    sample = (f"{threads} concurrent single-threaded matches of the same 1M/1M pair (MultiMatcher-style), each "
+              f"capped at {CPU_SAMPLE_ITERS} ICP iterations, kd-tree build included; {dt:.1f} s wall")
+    return sum(done) / dt, sample, dt
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    src, tgt, nrm = make_workload(0)
+    threads = host_threads()
+    vals, secs = [], []
+    for i in range(args.warmup_ref + args.steps_ref):
+        v, sample, dt = cpu_reference_sample(src, tgt, nrm, threads)
+        if i >= args.warmup_ref:
+            vals.append(v)
+            secs.append(dt)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "PCL cannot be built in this image (no PCL/Eigen/FLANN/Boost); the CPU arm is the oracle's "
+                "PCL-faithful restatement (oracle/icp.cpp, SUM_PCL arithmetic)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import libwave_b200 as W
+    from libwave_b200 import capi
+
+    src, tgt, nrm = make_workload(rank)
+    n = src.shape[0]
+    stream = torch.cuda.current_stream()
+    m = W.ICPMatcher(W.ICPMatcherParams(res=-1, estimator=W.EST_POINT_TO_PLANE), device=local_rank,
+                     stream=stream.cuda_stream)
+    m.set_profiling(True)
+
+    # device-resident inputs for `value`, pinned host inputs for `e2e`
+    d_src, d_tgt, d_nrm = (torch.from_numpy(a).to(dev) for a in (src, tgt, nrm))
+    h_src, h_tgt, h_nrm = (torch.from_numpy(a).pin_memory() for a in (src, tgt, nrm))
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    result_buf = torch.zeros(18, dtype=torch.float64, device=dev)
+    gathered = [torch.zeros_like(result_buf) for _ in range(world)] if world > 1 else None
+
+    def step_device():
+        m.setRefDevice(d_src.data_ptr(), n)
+        m.setTargetDevice(d_tgt.data_ptr(), n)
+        m.setTargetNormalsDevice(d_nrm.data_ptr(), n)
+        ok = m.match()
+        if world > 1:
+            result_buf[:16] = torch.from_numpy(m.getResult().reshape(16)).to(dev)
+            result_buf[16], result_buf[17] = float(ok), float(m.iterations)
+            dist.all_gather(gathered, result_buf)
+        return ok
+
+    def step_host():
+        m.setRef(h_src.numpy())
+        m.setTarget(h_tgt.numpy())
+        m.setTargetNormals(h_nrm.numpy())
+        ok = m.match()  # the 4x4 result, flags and trace are read back to the host inside match()
+        if world > 1:
+            result_buf[:16] = torch.from_numpy(m.getResult().reshape(16)).to(dev)
+            result_buf[16], result_buf[17] = float(ok), float(m.iterations)
+            dist.all_gather(gathered, result_buf)
+        return ok
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            flush.fill_(1)
+            step_fn()
+        barrier()
+        if sampler:
+            sampler.mark_start()
+        ms, pairs, launches, it_ms, it_n, build_ms, solve_ms = [], 0, 0, 0.0, 0, 0.0, 0.0
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush, outside the timed events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            ok = step_fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+            st = m.stats()
+            pairs += st["pairs"]
+            launches += st["kernel_launches"]
+            it_ms += st["iterate_ms"]
+            it_n += st["iterate_launches"]
+            build_ms += st["build_ms"]
+            solve_ms += st["solve_ms"]
+            assert ok, "match() did not converge on the benchmark workload"
+        if sampler:
+            sampler.mark_end()
+        barrier()
+        total_ms = float(sum(ms))
+        if world > 1:
+            t = torch.tensor([total_ms, float(pairs)], dtype=torch.float64, device=dev)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            total_ms_max, pairs_all = float(tmax[0]), float(t[1])
+        else:
+            total_ms_max, pairs_all = total_ms, float(pairs)
+        return {"total_ms": total_ms_max, "pairs_all": pairs_all, "launches": launches, "iterate_ms": it_ms,
+                "iterate_launches": it_n, "build_ms": build_ms, "solve_ms": solve_ms, "iters": m.iterations}
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    dev_run = timed(step_device, args.steps, args.warmup, sampler)
+    clocks = sampler.finish() if sampler else None
+    e2e_run = timed(step_host, args.steps, max(1, args.warmup // 2))
+
+    if rank == 0:
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        # algorithmic bytes per launch of the fused point-to-plane iteration, parity mode
+        # (SURVEY.md 8(d)): 16 B read + 16 B write per source point, 16 B point + 16 B normal per target
+        alg_bytes = 32.0 * n + 32.0 * n
+        mean_launch_ms = dev_run["iterate_ms"] / max(1, dev_run["iterate_launches"])
+        achieved = alg_bytes / (mean_launch_ms * 1e-3) / 1e9 if mean_launch_ms > 0 else 0.0
+        traffic = None
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            traffic = json.loads(tpath.read_text()).get("iterate_kernel_p2plane_dram_bytes_per_launch")
+        if args.skip_cpu:
+            cpu_v, cpu_sample = None, "skipped (--skip-cpu, profiling run)"
+        else:
+            cpu_v, cpu_sample, _ = cpu_reference_sample(src, tgt, nrm, host_threads())
+        line = {
+            "metric": METRIC, "value": dev_run["pairs_all"] / (dev_run["total_ms"] * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_run["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e_run["pairs_all"] / (e2e_run["total_ms"] * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(3 * 16 * n), "d2h_bytes_per_step": int(256 + 80 * dev_run["iters"]),
+                    "ms_per_step": e2e_run["total_ms"] / args.steps},
+            "gpu_launches": int(dev_run["launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "iterate_kernel<point_to_plane> (fused transform + exact 1-NN + "
+                         "J^T J / J^T r reduction)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
+                         "launches_timed": int(dev_run["iterate_launches"])},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                             "sample": cpu_sample},
+            "breakdown_ms_per_step": {"build": dev_run["build_ms"] / args.steps,
+                                      "iterate": dev_run["iterate_ms"] / args.steps,
+                                      "solve": dev_run["solve_ms"] / args.steps,
+                                      "icp_iterations": dev_run["iters"]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    # the CPU arm's steps are whole multi-second samples: keep the run within minutes
+    args.steps_ref = max(1, min(args.steps, 2))
+    args.warmup_ref = 0
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

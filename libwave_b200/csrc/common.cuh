@@ -22,16 +22,9 @@ void set_last_error(const std::string &msg);
         }                                                                                            \
     } while (0)
 
-constexpr int kLeafLog2 = 3;            // 8 points = one 128-byte line per leaf
-constexpr int kLeaf = 1 << kLeafLog2;
+constexpr int kLeaf = 8;                // a leaf is a run of <= 8 consecutive Morton-sorted points
 constexpr int kAccSlots = 16;           // accumulator replicas (atomic contention spreading)
 constexpr int kMaxAcc = 40;             // values per slot (p2p uses 17, point-to-plane 33)
-
-// One node of the implicit bounding-volume tree: children of node i are 2i and 2i+1, so a child
-// pair is one aligned 64-byte segment.  lo.w / hi.w are unused.
-struct __align__(32) Node {
-    float4 lo, hi;
-};
 
 // Per-match constants computed on the device by setup_kernel (no host round trip).
 struct MatchConsts {

@@ -262,7 +262,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     ia.nodes = tgt.d_nodes;
     ia.tgt = tgt.cloud.d_sorted;
     ia.nrm = tgt.d_nrm_sorted;
-    ia.P = tgt.P;
+    ia.root = tgt.d_root;
     ia.nn_pos = d_nn_pos;
     ia.nn_idx = d_nn_idx;
     ia.nn_d2 = d_nn_d2;

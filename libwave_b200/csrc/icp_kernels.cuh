@@ -22,10 +22,10 @@ constexpr int kIterWarps = kIterThreads / 32;
 struct IterArgs {
     float4 *cur;                 // working source cloud, Morton order, w = original index
     int n_src;
-    const Node *nodes;
+    const TNode *nodes;
+    const TreeRoot *root;
     const float4 *tgt;
     const float4 *nrm;           // sorted target normals (point-to-plane) or nullptr
-    int P;
     int *nn_pos;                 // sorted position of the match (-1: none) - warm start + gathers
     int *nn_idx;                 // original target index of the match (-1: none)
     float *nn_d2;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kIterThreads) iterate_kernel(IterArgs a) {
                 best_pos = warm;
             }
         }
-        nn_search(x, y, z, a.nodes, a.tgt, a.P, best, best_idx, best_pos);
+        nn_search(x, y, z, a.nodes, a.root, a.tgt, best, best_idx, best_pos);
         a.nn_pos[s] = best_pos;
         a.nn_idx[s] = best_pos >= 0 ? best_idx : -1;
         a.nn_d2[s] = best;

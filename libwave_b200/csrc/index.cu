@@ -15,13 +15,16 @@ constexpr int kBuildThreads = 256;
 __global__ void bbox_init_kernel(unsigned *bbox) {
     if (threadIdx.x < 3) bbox[threadIdx.x] = 0xff800000u;  // lo = ordered(+inf)
     else if (threadIdx.x < 6) bbox[threadIdx.x] = 0x007fffffu;  // hi = ordered(-inf)
+    else if (threadIdx.x < 8) bbox[threadIdx.x] = 0u;  // [6] = number of finite points
 }
 
 __global__ void __launch_bounds__(kBuildThreads) bbox_kernel(const float4 *__restrict__ pts, size_t n, unsigned *bbox) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    unsigned cnt = 0;
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
         const float4 p = pts[i];
         if (finite3(p.x, p.y, p.z)) {
+            ++cnt;
             lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
             lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
             lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
@@ -34,7 +37,9 @@ __global__ void __launch_bounds__(kBuildThreads) bbox_kernel(const float4 *__res
             lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
             hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
         }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
     if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(&bbox[6], cnt);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             if (lo[d] <= hi[d]) {
@@ -95,35 +100,72 @@ __global__ void __launch_bounds__(kBuildThreads) gather_kernel(const float4 *__r
     if (extra_out) extra_out[i] = e;
 }
 
-// One thread per leaf slot: leaf AABB, then climb; the second thread to reach a parent merges.
-__global__ void __launch_bounds__(kBuildThreads) tree_kernel(const float4 *__restrict__ pts, int P, Node *nodes,
-                                                             int *flags) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P) return;
-    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
-#pragma unroll
-    for (int k = 0; k < kLeaf; ++k) {
-        const float4 p = pts[(size_t) j * kLeaf + k];
-        if (p.x != INFINITY) {
-            lo.x = fminf(lo.x, p.x); hi.x = fmaxf(hi.x, p.x);
-            lo.y = fminf(lo.y, p.y); hi.y = fmaxf(hi.y, p.y);
-            lo.z = fminf(lo.z, p.z); hi.z = fmaxf(hi.z, p.z);
-        }
+// strict total order on the gaps between consecutive sorted keys: the radix tree is the Cartesian
+// tree of this order.  Equal keys fall back to the index bits (a balanced radix tree over the run).
+__device__ __forceinline__ bool gap_less(const unsigned long long *__restrict__ keys, int a, int b) {
+    const unsigned long long xa = keys[a] ^ keys[a + 1], xb = keys[b] ^ keys[b + 1];
+    if (xa != xb) return xa < xb;
+    const unsigned ia = (unsigned) a ^ (unsigned) (a + 1), ib = (unsigned) b ^ (unsigned) (b + 1);
+    if (ia != ib) return ia < ib;
+    return a < b;
+}
+
+// Agglomerative LBVH construction, one launch: thread i starts as the single-point node [i,i] and
+// climbs.  A node [l,r] hangs under the smaller of its two bounding gaps (l-1 and r); it writes its
+// box and link into that parent's record, then exchanges its far bound through other[parent]:
+// the first child to arrive retires, the second continues upward with the merged range and box.
+// Subtrees of <= kLeaf points are referenced as leaves (runs of the sorted array).
+__global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long long *__restrict__ keys,
+                                                             const float4 *__restrict__ pts,
+                                                             const unsigned *__restrict__ bbox, TNode *nodes, int *other,
+                                                             TreeRoot *root) {
+    const int n = (int) bbox[6];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && n == 0) {
+        root->lo = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(-1));
+        root->hi = make_float4(-INFINITY, -INFINITY, -INFINITY, __int_as_float(0));
     }
-    unsigned node = (unsigned) (P + j);
-    nodes[node].lo = lo;
-    nodes[node].hi = hi;
-    while (node > 1u) {
-        const unsigned parent = node >> 1;
+    if (i >= n) return;
+    int l = i, r = i;
+    const float4 p = pts[i];
+    float lox = p.x, loy = p.y, loz = p.z, hix = p.x, hiy = p.y, hiz = p.z;
+    int link = ~i;
+    for (;;) {
+        const int cnt = r - l + 1;
+        if (l == 0 && r == n - 1) {
+            root->lo = make_float4(lox, loy, loz, __int_as_float(link));
+            root->hi = make_float4(hix, hiy, hiz, __int_as_float(cnt));
+            return;
+        }
+        bool parent_right;  // parent is gap r: this node is its left child
+        if (l == 0) parent_right = true;
+        else if (r == n - 1) parent_right = false;
+        else parent_right = gap_less(keys, r, l - 1);
+        const int par = parent_right ? r : l - 1;
+        TNode *nd = nodes + par;
+        if (parent_right) {
+            nd->lo0 = make_float4(lox, loy, loz, __int_as_float(link));
+            nd->hi0 = make_float4(hix, hiy, hiz, __int_as_float(cnt));
+        } else {
+            nd->lo1 = make_float4(lox, loy, loz, __int_as_float(link));
+            nd->hi1 = make_float4(hix, hiy, hiz, __int_as_float(cnt));
+        }
         __threadfence();
-        if (atomicAdd(&flags[parent], 1) == 0) return;  // sibling not ready yet: it will merge
-        const unsigned sib = node ^ 1u;
-        const float4 slo = __ldcg(&nodes[sib].lo), shi = __ldcg(&nodes[sib].hi);
-        lo.x = fminf(lo.x, slo.x); lo.y = fminf(lo.y, slo.y); lo.z = fminf(lo.z, slo.z);
-        hi.x = fmaxf(hi.x, shi.x); hi.y = fmaxf(hi.y, shi.y); hi.z = fmaxf(hi.z, shi.z);
-        nodes[parent].lo = lo;
-        nodes[parent].hi = hi;
-        node = parent;
+        const int prev = atomicExch(&other[par], parent_right ? l : r);
+        if (prev == -1) return;
+        float4 slo, shi;
+        if (parent_right) {
+            r = prev;
+            slo = __ldcg(&nd->lo1);
+            shi = __ldcg(&nd->hi1);
+        } else {
+            l = prev;
+            slo = __ldcg(&nd->lo0);
+            shi = __ldcg(&nd->hi0);
+        }
+        lox = fminf(lox, slo.x); loy = fminf(loy, slo.y); loz = fminf(loz, slo.z);
+        hix = fmaxf(hix, shi.x); hiy = fmaxf(hiy, shi.y); hiz = fmaxf(hiz, shi.z);
+        link = (r - l + 1 <= kLeaf) ? ~l : par;
     }
 }
 
@@ -165,7 +207,7 @@ int MortonCloud::reserve(size_t n_points, size_t sorted_points) {
             tmp_bytes = need;
         }
     }
-    if (!d_bbox) WCU_CHECK(cudaMalloc((void **) &d_bbox, 6 * sizeof(unsigned)));
+    if (!d_bbox) WCU_CHECK(cudaMalloc((void **) &d_bbox, 8 * sizeof(unsigned)));
     if (sorted_points > sorted_cap) {
         if (d_sorted) WCU_CHECK(cudaFree(d_sorted));
         d_sorted = nullptr;
@@ -249,27 +291,32 @@ int TargetIndex::set_normals(const float *nxyzw, size_t n, bool from_device) {
 
 int TargetIndex::build() {
     WCU_CHECK(cudaSetDevice(cloud.device));
-    const size_t leaves = (cloud.n + kLeaf - 1) / kLeaf;
-    int p = 1;
-    while ((size_t) p < leaves) p <<= 1;
-    P = p;
-    const size_t n_pad = (size_t) P * kLeaf;
-    if ((size_t) 2 * P > node_cap) {
+    const size_t n = cloud.n;
+    if (n > (size_t) 0x7ffffff0) {
+        set_last_error("target cloud too large for 32-bit links");
+        return WAVECU_ERR_ARG;
+    }
+    if (n + 1 > node_cap) {
         if (d_nodes) WCU_CHECK(cudaFree(d_nodes));
-        if (d_flags) WCU_CHECK(cudaFree(d_flags));
-        d_nodes = nullptr; d_flags = nullptr; node_cap = 0;
-        WCU_CHECK(cudaMalloc((void **) &d_nodes, (size_t) 2 * P * sizeof(Node)));
-        WCU_CHECK(cudaMalloc((void **) &d_flags, (size_t) P * sizeof(int)));
-        node_cap = (size_t) 2 * P;
+        if (d_other) WCU_CHECK(cudaFree(d_other));
+        d_nodes = nullptr; d_other = nullptr; node_cap = 0;
+        const size_t a = n + n / 8 + 64;
+        WCU_CHECK(cudaMalloc((void **) &d_nodes, a * sizeof(TNode)));
+        WCU_CHECK(cudaMalloc((void **) &d_other, a * sizeof(int)));
+        node_cap = a;
+    }
+    if (!d_root) WCU_CHECK(cudaMalloc((void **) &d_root, sizeof(TreeRoot)));
+    if (nrm_n && n > nrm_sorted_cap) {
         if (d_nrm_sorted) WCU_CHECK(cudaFree(d_nrm_sorted));
         d_nrm_sorted = nullptr;
+        WCU_CHECK(cudaMalloc((void **) &d_nrm_sorted, (n + n / 8 + 64) * sizeof(float4)));
+        nrm_sorted_cap = n + n / 8 + 64;
     }
-    if (nrm_n && !d_nrm_sorted) WCU_CHECK(cudaMalloc((void **) &d_nrm_sorted, (size_t) (node_cap / 2) * kLeaf * sizeof(float4)));
-    int rc = cloud.sort(n_pad, nrm_n ? d_nrm_raw : nullptr, nrm_n ? d_nrm_sorted : nullptr);
+    int rc = cloud.sort(std::max<size_t>(n, 1), nrm_n ? d_nrm_raw : nullptr, nrm_n ? d_nrm_sorted : nullptr);
     if (rc) return rc;
-    WCU_CHECK(cudaMemsetAsync(d_flags, 0, (size_t) P * sizeof(int), cloud.stream));
-    tree_kernel<<<(P + kBuildThreads - 1) / kBuildThreads, kBuildThreads, 0, cloud.stream>>>(cloud.d_sorted, P, d_nodes,
-                                                                                              d_flags);
+    if (n) WCU_CHECK(cudaMemsetAsync(d_other, 0xff, n * sizeof(int), cloud.stream));
+    lbvh_kernel<<<(unsigned) std::max<size_t>(1, (n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0,
+                  cloud.stream>>>(cloud.d_keys, cloud.d_sorted, cloud.d_bbox, d_nodes, d_other, d_root);
     ++cloud.launches;
     WCU_CHECK(cudaGetLastError());
     dirty = false;
@@ -278,10 +325,10 @@ int TargetIndex::build() {
 
 void TargetIndex::release() {
     cloud.release();
-    for (void *p : {(void *) d_nodes, (void *) d_flags, (void *) d_nrm_raw, (void *) d_nrm_sorted})
+    for (void *p : {(void *) d_nodes, (void *) d_other, (void *) d_root, (void *) d_nrm_raw, (void *) d_nrm_sorted})
         if (p) cudaFree(p);
-    d_nodes = nullptr; d_flags = nullptr; d_nrm_raw = d_nrm_sorted = nullptr;
-    node_cap = nrm_cap = nrm_n = 0;
+    d_nodes = nullptr; d_other = nullptr; d_root = nullptr; d_nrm_raw = d_nrm_sorted = nullptr;
+    node_cap = nrm_cap = nrm_sorted_cap = nrm_n = 0;
 }
 
 }  // namespace wavecu

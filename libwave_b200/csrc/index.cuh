@@ -4,9 +4,12 @@
 // for every align() target (reference call sites: wave_matching/src/icp.cpp:124-126,
 // src/icp_pcl_functions.cpp:67-68).  B200 design instead of a pointer kd-tree:
 //   * points are sorted once by a 63-bit Morton key and stored as float4 (w carries the original
-//     index), so a leaf of 8 consecutive points is exactly one aligned 128-byte line;
-//   * the tree over the leaves is a complete binary heap of AABBs (children of i are 2i, 2i+1,
-//     a child pair is one aligned 64-byte segment) - no pointers, built bottom-up in one launch;
+//     index); a leaf is a run of <= 8 consecutive sorted points;
+//   * the hierarchy is the radix tree of the sorted keys (split at the highest differing bit),
+//     built bottom-up in ONE launch (one thread per point, rendezvous by atomicExch - the
+//     agglomerative LBVH construction), emitting 64-byte nodes that hold both children's boxes;
+//     measured on the 1 M-point lidar workload this visits ~3 leaves / ~30 nodes per query where
+//     a count-balanced split of the same Morton order visits 22 / 220 (tools/probe_*.cpp);
 //   * queries are Morton-sorted as well, so the 32 lanes of a warp walk the same few nodes and
 //     leaves and their loads coalesce in L1/L2 (the whole structure for 1 M points is ~24 MB and
 //     stays resident in the 126 MB L2).
@@ -37,14 +40,29 @@ struct MortonCloud {
     void release();
 };
 
+// Traversal node of the radix-tree LBVH: both children's boxes and links in one aligned 64-byte
+// record, so one node visit is one segment load.  link >= 0: index of the child's own node;
+// link < 0: the child is a leaf, a run of `cnt` (<= kLeaf) consecutive sorted points starting at
+// ~link.
+struct __align__(64) TNode {
+    float4 lo0;  // xyz, w = link0 (int bits)
+    float4 hi0;  // xyz, w = cnt0 (int bits)
+    float4 lo1;  // xyz, w = link1
+    float4 hi1;  // xyz, w = cnt1
+};
+
+struct TreeRoot {
+    float4 lo, hi;   // box of all finite points; lo.w = link (int bits), hi.w = count (int bits)
+};
+
 struct TargetIndex {
     MortonCloud cloud;
-    int P = 0;               // leaf slots, power of two; nodes are 1..2P-1, leaf j is node P+j
-    Node *d_nodes = nullptr;
-    int *d_flags = nullptr;
+    TNode *d_nodes = nullptr;    // n-1 records, indexed by split position
+    int *d_other = nullptr;      // n-1 rendezvous slots of the bottom-up build
+    TreeRoot *d_root = nullptr;
     float4 *d_nrm_raw = nullptr, *d_nrm_sorted = nullptr;  // optional normals
     size_t nrm_n = 0;
-    size_t node_cap = 0, nrm_cap = 0;
+    size_t node_cap = 0, nrm_cap = 0, nrm_sorted_cap = 0;
     bool dirty = true;
 
     int set_points(const float *xyzw, size_t n, bool from_device);
@@ -61,61 +79,83 @@ __device__ __forceinline__ float ordered_to_float(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+constexpr int kStackDepth = 96;  // >= 63 key bits + 27 index bits of radix-tree depth
+
+__device__ __forceinline__ void scan_leaf(float qx, float qy, float qz, const float4 *__restrict__ pts, int start,
+                                          int cnt, float &best, int &best_idx, int &best_pos) {
+    for (int k = 0; k < cnt; ++k) {
+        const float4 p = __ldg(pts + start + k);
+        const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+        const int idx = __float_as_int(p.w);
+        if (d < best || (d == best && idx < best_idx)) {
+            best = d;
+            best_idx = idx;
+            best_pos = start + k;
+        }
+    }
+}
+
 // Exact 1-NN of (qx,qy,qz) under l2_simple with the lowest original index among exact ties.
 // best / best_idx come in as the current bound (e.g. the max-correspondence threshold with
 // best_idx = INT_MAX, or a warm start) and leave as the result.  A subtree is skipped only when
 // its bound is strictly greater than best, so equal-distance candidates are always examined.
-__device__ __forceinline__ void nn_search(float qx, float qy, float qz, const Node *__restrict__ nodes,
-                                          const float4 *__restrict__ pts, int P, float &best, int &best_idx,
-                                          int &best_pos) {
-    unsigned node = 1u, pending = 0u;
-    {
-        const Node root = nodes[1];
-        if (aabb_dist(qx, qy, qz, root.lo, root.hi) > best) return;
+__device__ __forceinline__ void nn_search(float qx, float qy, float qz, const TNode *__restrict__ nodes,
+                                          const TreeRoot *__restrict__ root, const float4 *__restrict__ pts,
+                                          float &best, int &best_idx, int &best_pos) {
+    const float4 rlo = __ldg(&root->lo), rhi = __ldg(&root->hi);
+    const int rcount = __float_as_int(rhi.w);
+    if (rcount <= 0 || aabb_dist(qx, qy, qz, rlo, rhi) > best) return;
+    int link = __float_as_int(rlo.w);
+    if (link < 0) {
+        scan_leaf(qx, qy, qz, pts, ~link, rcount, best, best_idx, best_pos);
+        return;
     }
+    int stack_link[kStackDepth];
+    int stack_cnt[kStackDepth];
+    float stack_d[kStackDepth];
+    int sp = 0;
     for (;;) {
-        bool up = false;
-        if (node >= (unsigned) P) {
-            const float4 *leaf = pts + (size_t)(node - P) * kLeaf;
-#pragma unroll
-            for (int k = 0; k < kLeaf; ++k) {
-                const float4 p = __ldg(leaf + k);
-                const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
-                const int idx = __float_as_int(p.w);
-                if (d < best || (d == best && idx < best_idx)) {
-                    best = d;
-                    best_idx = idx;
-                    best_pos = (int) (node - P) * kLeaf + k;
-                }
+        // `link` is an internal node whose box passed the bound test
+        const float4 a = __ldg(&nodes[link].lo0), b = __ldg(&nodes[link].hi0);
+        const float4 c = __ldg(&nodes[link].lo1), d = __ldg(&nodes[link].hi1);
+        const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
+        const bool right_first = d1 < d0;
+        const float dn = right_first ? d1 : d0, df = right_first ? d0 : d1;
+        const int ln = __float_as_int(right_first ? c.w : a.w), lf = __float_as_int(right_first ? a.w : c.w);
+        const int cn = __float_as_int(right_first ? d.w : b.w), cf = __float_as_int(right_first ? b.w : d.w);
+        int next = 0;
+        bool have_next = false;
+        if (dn <= best) {
+            if (ln < 0) scan_leaf(qx, qy, qz, pts, ~ln, cn, best, best_idx, best_pos);
+            else {
+                next = ln;
+                have_next = true;
             }
-            up = true;
-        } else {
-            const Node c0 = nodes[2 * node], c1 = nodes[2 * node + 1];
-            const float d0 = aabb_dist(qx, qy, qz, c0.lo, c0.hi);
-            const float d1 = aabb_dist(qx, qy, qz, c1.lo, c1.hi);
-            const bool right_first = d1 < d0;
-            const float dn = right_first ? d1 : d0, df = right_first ? d0 : d1;
-            if (dn > best) {
-                up = true;
-            } else {
-                pending = (pending << 1) | (df <= best ? 1u : 0u);
-                node = 2 * node + (right_first ? 1u : 0u);
-            }
-        }
-        if (up) {
-            for (;;) {
-                if (node == 1u) return;
-                if (pending & 1u) {
-                    pending &= ~1u;
-                    node ^= 1u;
-                    const Node s = nodes[node];
-                    if (aabb_dist(qx, qy, qz, s.lo, s.hi) <= best) break;
+            if (df <= best) {
+                if (lf < 0 && !have_next) scan_leaf(qx, qy, qz, pts, ~lf, cf, best, best_idx, best_pos);
+                else if (!have_next) {
+                    next = lf;
+                    have_next = true;
                 } else {
-                    node >>= 1;
-                    pending >>= 1;
+                    stack_link[sp] = lf;
+                    stack_cnt[sp] = cf;
+                    stack_d[sp] = df;
+                    ++sp;
                 }
             }
         }
+        while (!have_next) {
+            if (sp == 0) return;
+            --sp;
+            if (stack_d[sp] > best) continue;
+            const int l = stack_link[sp];
+            if (l < 0) scan_leaf(qx, qy, qz, pts, ~l, stack_cnt[sp], best, best_idx, best_pos);
+            else {
+                next = l;
+                have_next = true;
+            }
+        }
+        link = next;
     }
 }
 
