@@ -289,15 +289,16 @@ def run_ours(args):
             peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # algorithmic bytes per launch of the fused point-to-plane iteration, parity mode
-        # (SURVEY.md 8(d)): 16 B read + 16 B write per source point, 16 B point + 16 B normal per target
-        alg_bytes = 32.0 * n + 32.0 * n
+        # algorithmic bytes per launch of the NN-correspondence kernel:
+        # 16 B query + 8 B result (int32 index + fp32 d2) per source point, 16 B per target point.
+        # (The kernel also writes the moved working cloud back, 16 B/point, which is not counted.)
+        alg_bytes = 24.0 * n + 16.0 * n
         mean_launch_ms = dev_run["iterate_ms"] / max(1, dev_run["iterate_launches"])
         achieved = alg_bytes / (mean_launch_ms * 1e-3) / 1e9 if mean_launch_ms > 0 else 0.0
         traffic = None
         tpath = ROOT / "profiles" / "traffic.json"
         if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get("iterate_kernel_p2plane_dram_bytes_per_launch")
+            traffic = json.loads(tpath.read_text()).get("correspond_kernel_dram_bytes_per_launch")
         if args.skip_cpu:
             cpu_v, cpu_sample = None, "skipped (--skip-cpu, profiling run)"
         else:
@@ -312,16 +313,16 @@ def run_ours(args):
                     "ms_per_step": e2e_run["total_ms"] / args.steps},
             "gpu_launches": int(dev_run["launches"]),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "iterate_kernel<point_to_plane> (fused transform + exact 1-NN + "
-                         "J^T J / J^T r reduction)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "correspond_kernel (in-place incremental transform + exact 1-NN "
+                         "correspondence search over the LBVH)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
                          "launches_timed": int(dev_run["iterate_launches"])},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": host_threads(), "kind": "port",
                              "sample": cpu_sample},
             "breakdown_ms_per_step": {"build": dev_run["build_ms"] / args.steps,
-                                      "iterate": dev_run["iterate_ms"] / args.steps,
-                                      "solve": dev_run["solve_ms"] / args.steps,
+                                      "correspond": dev_run["iterate_ms"] / args.steps,
+                                      "reduce_solve": dev_run["solve_ms"] / args.steps,
                                       "icp_iterations": dev_run["iters"]},
         }
         print(json.dumps(line))

@@ -117,8 +117,8 @@ int wavecu_icp_info(wavecu_icp *h, int method, double info_out[36]);
  * handle's stream when profiling is enabled (adds one event pair per kernel). */
 typedef struct {
     double build_ms;        /* search-structure build (sort + tree) */
-    double iterate_ms;      /* sum over iterations of the fused correspondence kernel */
-    double solve_ms;        /* sum of the estimator/convergence kernel */
+    double iterate_ms;      /* sum over iterations of the correspondence kernel (transform + 1-NN) */
+    double solve_ms;        /* sum of the reduction + estimator/convergence kernels */
     double total_ms;        /* whole align()/match() on the stream */
     long long iterate_launches;
     long long kernel_launches; /* every kernel this library launched in the call */

@@ -270,8 +270,9 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     ia.mc = d_mc;
     ia.acc = d_acc;
     SolveArgs so{d_st, d_mc, d_acc, d_trace, max_iter, prm.t_eps, prm.fit_eps};
-    const unsigned grid = (unsigned) std::max<size_t>(1, (n_src + kIterThreads * kQueriesPerThread - 1) /
-                                                             (kIterThreads * kQueriesPerThread));
+    const unsigned grid_nn = (unsigned) std::max<size_t>(1, (n_src + kIterThreads - 1) / kIterThreads);
+    const unsigned grid_red = (unsigned) std::max<size_t>(
+        1, (n_src + kReduceThreads * kReducePerThread - 1) / (kReduceThreads * kReducePerThread));
     std::vector<cudaEvent_t> it_ev;
     int launched = 0;
     bool finished = (n_src == 0 || n_tgt == 0);  // initCompute fails -> converged_ = false
@@ -280,18 +281,18 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             it_ev.push_back(next_event());
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
         }
-        if (prm.estimator == WAVECU_EST_POINT_TO_PLANE)
-            iterate_kernel<WAVECU_EST_POINT_TO_PLANE><<<grid, kIterThreads, 0, stream>>>(ia);
-        else
-            iterate_kernel<WAVECU_EST_SVD><<<grid, kIterThreads, 0, stream>>>(ia);
+        correspond_kernel<<<grid_nn, kIterThreads, 0, stream>>>(ia);
         if (profiling) {
             it_ev.push_back(next_event());
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
         }
-        if (prm.estimator == WAVECU_EST_POINT_TO_PLANE)
+        if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
+            reduce_kernel<WAVECU_EST_POINT_TO_PLANE><<<grid_red, kReduceThreads, 0, stream>>>(ia);
             solve_kernel<WAVECU_EST_POINT_TO_PLANE><<<1, 32, 0, stream>>>(so);
-        else
+        } else {
+            reduce_kernel<WAVECU_EST_SVD><<<grid_red, kReduceThreads, 0, stream>>>(ia);
             solve_kernel<WAVECU_EST_SVD><<<1, 32, 0, stream>>>(so);
+        }
         if (profiling) {
             it_ev.push_back(next_event());
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
@@ -323,7 +324,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     result_n_src = n_src;
 
     stats.iterate_launches = last.iter;
-    stats.kernel_launches = (src.launches + tgt.cloud.launches - launches0) + extra_launches + 2LL * launched;
+    stats.kernel_launches = (src.launches + tgt.cloud.launches - launches0) + extra_launches + 3LL * launched;
     stats.pairs = (long long) last.iter * (long long) n_src;
     if (profiling) {
         float ms = 0;

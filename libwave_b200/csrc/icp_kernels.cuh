@@ -1,9 +1,11 @@
 // Device side of one ICP iteration (pcl::IterativeClosestPoint::computeTransformation, SURVEY.md
 // Appendix A.3-A.5; reference call sites wave_matching/src/icp.cpp:95,116,126).
 //
-//   iterate_kernel  fuses, per source point: the in-place incremental fp32 transform of the working
-//                   cloud (A.3.2), the exact 1-NN correspondence search with the max-distance test
-//                   (A.3.1), and the estimator's reduction - {n, sum p, sum q, sum q p^T, sum d2}
+//   correspond_kernel  per source point: the in-place incremental fp32 transform of the working
+//                   cloud (A.3.2) fused with the exact 1-NN correspondence search and max-distance
+//                   test (A.3.1).  Kept lean in registers (no accumulators live across the tree
+//                   walk) so that 8+ CTAs stay resident per SM - the walk is latency bound.
+//   reduce_kernel   streaming pass over the correspondences: {n, sum p, sum q, sum q p^T, sum d2}
 //                   for the SVD estimator (A.4) or the 21+6 entries of J^T J / J^T r for
 //                   point-to-plane (8(a) A7) - as exact 128-bit fixed-point sums (DESIGN.md
 //                   "Estimator arithmetic"): warp butterfly -> block -> a few 64-bit atomics.
@@ -15,9 +17,10 @@
 
 namespace wavecu {
 
-constexpr int kIterThreads = 128;
-constexpr int kQueriesPerThread = 4;
-constexpr int kIterWarps = kIterThreads / 32;
+constexpr int kIterThreads = 128;       // correspondence kernel: one query per thread
+constexpr int kReduceThreads = 256;     // reduction kernel
+constexpr int kReducePerThread = 8;
+constexpr int kReduceWarps = kReduceThreads / 32;
 
 struct IterArgs {
     float4 *cur;                 // working source cloud, Morton order, w = original index
@@ -71,16 +74,53 @@ __device__ __forceinline__ void warp_reduce_transpose(long long (&v)[NV], int la
     for (; bit >= 1; bit >>= 1) v[0] += shfl_xor_ll(v[0], bit);
 }
 
+// Correspondence kernel (A.3.2 + A.3.1): cur <- T_inc (x) cur in place, then the exact 1-NN of the
+// moved point within the max-correspondence distance, warm-started from the previous match.
+__global__ void __launch_bounds__(kIterThreads, 8) correspond_kernel(IterArgs a) {
+    if (a.st->done) return;
+    __shared__ float sT[12];
+    if (threadIdx.x < 12) sT[threadIdx.x] = a.st->T_inc[threadIdx.x];
+    __syncthreads();
+    const int s = blockIdx.x * kIterThreads + threadIdx.x;
+    if (s >= a.n_src) return;
+    const float4 c = a.cur[s];
+    if (!finite3(c.x, c.y, c.z)) {  // pads and non-finite source points take no part
+        a.nn_pos[s] = -1;
+        a.nn_idx[s] = -1;
+        a.nn_d2[s] = INFINITY;
+        return;
+    }
+    const float x = xform_row(sT + 0, c.x, c.y, c.z);
+    const float y = xform_row(sT + 4, c.x, c.y, c.z);
+    const float z = xform_row(sT + 8, c.x, c.y, c.z);
+    a.cur[s] = make_float4(x, y, z, c.w);
+
+    float best = a.mc->thr;
+    int best_idx = 0x7fffffff, best_pos = -1;
+    const int warm = a.nn_pos[s];
+    if (warm >= 0) {
+        const float4 p = __ldg(a.tgt + warm);
+        const float d = l2_simple(x, y, z, p.x, p.y, p.z);
+        if (d <= best) {
+            best = d;
+            best_idx = __float_as_int(p.w);
+            best_pos = warm;
+        }
+    }
+    nn_search(x, y, z, a.nodes, a.root, a.tgt, best, best_idx, best_pos);
+    a.nn_pos[s] = best_pos;
+    a.nn_idx[s] = best_pos >= 0 ? best_idx : -1;
+    a.nn_d2[s] = best;
+}
+
+// Estimator reduction over the correspondences (A.4 / 8(a) A7): a streaming pass - 16 B working
+// point + 4 B match position + 4 B distance per source point, 16 B (+16 B normal) gathered per
+// pair - into exact 128-bit fixed-point sums.
 template <int EST>
-__global__ void __launch_bounds__(kIterThreads) iterate_kernel(IterArgs a) {
+__global__ void __launch_bounds__(kReduceThreads) reduce_kernel(IterArgs a) {
     constexpr int NV = EstTraits<EST>::NV;
     if (a.st->done) return;
-    __shared__ long long s_part[kIterWarps][NV + 1];
-
-    float T[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) T[i] = a.st->T_inc[i];
-    const float thr = a.mc->thr;
+    __shared__ long long s_part[kReduceWarps][NV + 1];
     const double s_lin = a.mc->s_lin, s_quad = a.mc->s_quad, s_d2 = a.mc->s_d2, s_plane = a.mc->s_plane;
 
     long long v[NV];
@@ -88,43 +128,18 @@ __global__ void __launch_bounds__(kIterThreads) iterate_kernel(IterArgs a) {
     for (int i = 0; i < NV; ++i) v[i] = 0;
     int count = 0;
 
-    const int base = blockIdx.x * (kIterThreads * kQueriesPerThread) + threadIdx.x;
-#pragma unroll 1
-    for (int r = 0; r < kQueriesPerThread; ++r) {
-        const int s = base + r * kIterThreads;
+    const int base = blockIdx.x * (kReduceThreads * kReducePerThread) + threadIdx.x;
+#pragma unroll 2
+    for (int r = 0; r < kReducePerThread; ++r) {
+        const int s = base + r * kReduceThreads;
         if (s >= a.n_src) break;
-        float4 c = a.cur[s];
-        if (!finite3(c.x, c.y, c.z)) {  // pads and non-finite source points take no part
-            a.nn_pos[s] = -1;
-            a.nn_idx[s] = -1;
-            a.nn_d2[s] = INFINITY;
-            continue;
-        }
-        const float x = xform_row(T + 0, c.x, c.y, c.z);
-        const float y = xform_row(T + 4, c.x, c.y, c.z);
-        const float z = xform_row(T + 8, c.x, c.y, c.z);
-        a.cur[s] = make_float4(x, y, z, c.w);
-
-        float best = thr;
-        int best_idx = 0x7fffffff, best_pos = -1;
-        const int warm = a.nn_pos[s];
-        if (warm >= 0) {
-            const float4 p = __ldg(a.tgt + warm);
-            const float d = l2_simple(x, y, z, p.x, p.y, p.z);
-            if (d <= best) {
-                best = d;
-                best_idx = __float_as_int(p.w);
-                best_pos = warm;
-            }
-        }
-        nn_search(x, y, z, a.nodes, a.root, a.tgt, best, best_idx, best_pos);
-        a.nn_pos[s] = best_pos;
-        a.nn_idx[s] = best_pos >= 0 ? best_idx : -1;
-        a.nn_d2[s] = best;
-        if (best_pos < 0) continue;
-
+        const int pos = a.nn_pos[s];
+        if (pos < 0) continue;
+        const float4 c = a.cur[s];
+        const float best = a.nn_d2[s];
+        const float x = c.x, y = c.y, z = c.z;
         ++count;
-        const float4 q = __ldg(a.tgt + best_pos);
+        const float4 q = __ldg(a.tgt + pos);
         if (EST == WAVECU_EST_SVD) {
             const double px = x, py = y, pz = z, qx = q.x, qy = q.y, qz = q.z;
             v[0] += __double2ll_rn(px * s_lin);
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(kIterThreads) iterate_kernel(IterArgs a) {
             v[15] += __double2ll_rn((double) best * s_d2);
         } else {
             v[27] += __double2ll_rn((double) best * s_d2);
-            const float4 nn = __ldg(a.nrm + best_pos);
+            const float4 nn = __ldg(a.nrm + pos);
             if (finite3(nn.x, nn.y, nn.z)) {
                 // TransformationEstimationPointToPlaneLLS: a, b, c, d evaluated in fp32
                 double J[6];
@@ -181,7 +196,7 @@ __global__ void __launch_bounds__(kIterThreads) iterate_kernel(IterArgs a) {
     if (threadIdx.x <= NV) {
         __int128 tot = 0;
 #pragma unroll
-        for (int w = 0; w < kIterWarps; ++w) tot += (__int128) s_part[w][threadIdx.x];
+        for (int w = 0; w < kReduceWarps; ++w) tot += (__int128) s_part[w][threadIdx.x];
         if (tot != 0) {
             Acc128 *dst = a.acc + (blockIdx.x % kAccSlots) * kMaxAcc + threadIdx.x;
             atomic_add128(dst, (unsigned long long) tot, (long long) (tot >> 64));

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
     int l = i, r = i;
     const float4 p = pts[i];
     float lox = p.x, loy = p.y, loz = p.z, hix = p.x, hiy = p.y, hiz = p.z;
-    int link = ~i;
+    int link = make_leaf_link(i, 1);
     for (;;) {
         const int cnt = r - l + 1;
         if (l == 0 && r == n - 1) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
         }
         lox = fminf(lox, slo.x); loy = fminf(loy, slo.y); loz = fminf(loz, slo.z);
         hix = fmaxf(hix, shi.x); hiy = fmaxf(hiy, shi.y); hiz = fmaxf(hiz, shi.z);
-        link = (r - l + 1 <= kLeaf) ? ~l : par;
+        link = (r - l + 1 <= kLeaf) ? make_leaf_link(l, r - l + 1) : par;
     }
 }
 
@@ -292,8 +292,8 @@ int TargetIndex::set_normals(const float *nxyzw, size_t n, bool from_device) {
 int TargetIndex::build() {
     WCU_CHECK(cudaSetDevice(cloud.device));
     const size_t n = cloud.n;
-    if (n > (size_t) 0x7ffffff0) {
-        set_last_error("target cloud too large for 32-bit links");
+    if (n >= ((size_t) 1 << 27)) {
+        set_last_error("target cloud too large for 27-bit leaf links (>= 134M points)");
         return WAVECU_ERR_ARG;
     }
     if (n + 1 > node_cap) {

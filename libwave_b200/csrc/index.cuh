@@ -42,8 +42,7 @@ struct MortonCloud {
 
 // Traversal node of the radix-tree LBVH: both children's boxes and links in one aligned 64-byte
 // record, so one node visit is one segment load.  link >= 0: index of the child's own node;
-// link < 0: the child is a leaf, a run of `cnt` (<= kLeaf) consecutive sorted points starting at
-// ~link.
+// link < 0: the child is a leaf, a run of <= kLeaf consecutive sorted points (make_leaf_link).
 struct __align__(64) TNode {
     float4 lo0;  // xyz, w = link0 (int bits)
     float4 hi0;  // xyz, w = cnt0 (int bits)
@@ -80,17 +79,30 @@ __device__ __forceinline__ float ordered_to_float(unsigned u) {
 }
 
 constexpr int kStackDepth = 96;  // >= 63 key bits + 27 index bits of radix-tree depth
+constexpr int kLinkDone = (int) 0x80000000;
 
-__device__ __forceinline__ void scan_leaf(float qx, float qy, float qz, const float4 *__restrict__ pts, int start,
-                                          int cnt, float &best, int &best_idx, int &best_pos) {
-    for (int k = 0; k < cnt; ++k) {
-        const float4 p = __ldg(pts + start + k);
-        const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
-        const int idx = __float_as_int(p.w);
-        if (d < best || (d == best && idx < best_idx)) {
-            best = d;
-            best_idx = idx;
-            best_pos = start + k;
+// Leaf link: -1 - (start | (cnt-1) << 27); start < 2^27 points, cnt <= 16.
+__host__ __device__ __forceinline__ int make_leaf_link(int start, int cnt) { return -1 - (start | ((cnt - 1) << 27)); }
+__device__ __forceinline__ int leaf_start(int link) { return (-1 - link) & 0x7ffffff; }
+__device__ __forceinline__ int leaf_count(int link) { return (((-1 - link) >> 27) & 15) + 1; }
+
+__device__ __forceinline__ void scan_leaf(float qx, float qy, float qz, const float4 *__restrict__ pts, int link,
+                                          float &best, int &best_idx, int &best_pos) {
+    const int start = leaf_start(link), cnt = leaf_count(link);
+    float4 p[kLeaf];
+#pragma unroll
+    for (int k = 0; k < kLeaf; ++k)
+        if (k < cnt) p[k] = __ldg(pts + start + k);
+#pragma unroll
+    for (int k = 0; k < kLeaf; ++k) {
+        if (k < cnt) {
+            const float d = l2_simple(qx, qy, qz, p[k].x, p[k].y, p[k].z);
+            const int idx = __float_as_int(p[k].w);
+            if (d < best || (d == best && idx < best_idx)) {
+                best = d;
+                best_idx = idx;
+                best_pos = start + k;
+            }
         }
     }
 }
@@ -99,63 +111,53 @@ __device__ __forceinline__ void scan_leaf(float qx, float qy, float qz, const fl
 // best / best_idx come in as the current bound (e.g. the max-correspondence threshold with
 // best_idx = INT_MAX, or a warm start) and leave as the result.  A subtree is skipped only when
 // its bound is strictly greater than best, so equal-distance candidates are always examined.
+// "while-while" traversal: all lanes of a warp first descend through internal nodes until each
+// holds a leaf (or is done), then all scan their leaves together.
 __device__ __forceinline__ void nn_search(float qx, float qy, float qz, const TNode *__restrict__ nodes,
                                           const TreeRoot *__restrict__ root, const float4 *__restrict__ pts,
                                           float &best, int &best_idx, int &best_pos) {
     const float4 rlo = __ldg(&root->lo), rhi = __ldg(&root->hi);
-    const int rcount = __float_as_int(rhi.w);
-    if (rcount <= 0 || aabb_dist(qx, qy, qz, rlo, rhi) > best) return;
+    if (__float_as_int(rhi.w) <= 0 || aabb_dist(qx, qy, qz, rlo, rhi) > best) return;
     int link = __float_as_int(rlo.w);
-    if (link < 0) {
-        scan_leaf(qx, qy, qz, pts, ~link, rcount, best, best_idx, best_pos);
-        return;
-    }
     int stack_link[kStackDepth];
-    int stack_cnt[kStackDepth];
     float stack_d[kStackDepth];
     int sp = 0;
     for (;;) {
-        // `link` is an internal node whose box passed the bound test
-        const float4 a = __ldg(&nodes[link].lo0), b = __ldg(&nodes[link].hi0);
-        const float4 c = __ldg(&nodes[link].lo1), d = __ldg(&nodes[link].hi1);
-        const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
-        const bool right_first = d1 < d0;
-        const float dn = right_first ? d1 : d0, df = right_first ? d0 : d1;
-        const int ln = __float_as_int(right_first ? c.w : a.w), lf = __float_as_int(right_first ? a.w : c.w);
-        const int cn = __float_as_int(right_first ? d.w : b.w), cf = __float_as_int(right_first ? b.w : d.w);
-        int next = 0;
-        bool have_next = false;
-        if (dn <= best) {
-            if (ln < 0) scan_leaf(qx, qy, qz, pts, ~ln, cn, best, best_idx, best_pos);
-            else {
-                next = ln;
-                have_next = true;
-            }
-            if (df <= best) {
-                if (lf < 0 && !have_next) scan_leaf(qx, qy, qz, pts, ~lf, cf, best, best_idx, best_pos);
-                else if (!have_next) {
-                    next = lf;
-                    have_next = true;
-                } else {
+        while (link >= 0) {
+            const float4 a = __ldg(&nodes[link].lo0), b = __ldg(&nodes[link].hi0);
+            const float4 c = __ldg(&nodes[link].lo1), d = __ldg(&nodes[link].hi1);
+            const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
+            const bool right_first = d1 < d0;
+            const float dn = right_first ? d1 : d0, df = right_first ? d0 : d1;
+            const int ln = __float_as_int(right_first ? c.w : a.w), lf = __float_as_int(right_first ? a.w : c.w);
+            if (dn <= best) {
+                if (df <= best) {
                     stack_link[sp] = lf;
-                    stack_cnt[sp] = cf;
                     stack_d[sp] = df;
                     ++sp;
                 }
+                link = ln;
+            } else {
+                link = kLinkDone;
+                while (sp > 0) {
+                    --sp;
+                    if (stack_d[sp] <= best) {
+                        link = stack_link[sp];
+                        break;
+                    }
+                }
             }
         }
-        while (!have_next) {
-            if (sp == 0) return;
+        if (link == kLinkDone) return;
+        scan_leaf(qx, qy, qz, pts, link, best, best_idx, best_pos);
+        link = kLinkDone;
+        while (sp > 0) {
             --sp;
-            if (stack_d[sp] > best) continue;
-            const int l = stack_link[sp];
-            if (l < 0) scan_leaf(qx, qy, qz, pts, ~l, stack_cnt[sp], best, best_idx, best_pos);
-            else {
-                next = l;
-                have_next = true;
+            if (stack_d[sp] <= best) {
+                link = stack_link[sp];
+                break;
             }
         }
-        link = next;
     }
 }
 
