@@ -6,7 +6,9 @@ import ctypes as C
 import pathlib
 
 _DIR = pathlib.Path(__file__).resolve().parent
-SO = _DIR / "libwavecu.so"
+import os
+
+SO = _DIR / os.environ.get("WAVECU_SO", "libwavecu.so")  # WAVECU_SO: tuning builds only
 
 EST_SVD, EST_POINT_TO_PLANE = 0, 1
 INFO_LUM, INFO_CENSI, INFO_LUMOLD = 0, 1, 2

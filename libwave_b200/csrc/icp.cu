@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -166,8 +167,12 @@ int IcpHandle::init() {
         WCU_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         own_stream = true;
     }
+    src.key_bits = 10;  // the source order only has to be spatially coherent: 31 sorted bits, 4 passes
+    if (const char *e = getenv("WAVECU_SRC_BITS")) src.key_bits = std::max(1, std::min(21, atoi(e)));  // tuning knob
+    if (const char *e = getenv("WAVECU_TGT_BITS")) tgt.cloud.key_bits = std::max(1, std::min(21, atoi(e)));
     src.device = tgt.cloud.device = device;
     src.stream = tgt.cloud.stream = stream;
+    cudaFuncSetAttribute(correspond_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     WCU_CHECK(cudaMalloc((void **) &d_mc, sizeof(MatchConsts)));
     WCU_CHECK(cudaMalloc((void **) &d_st, sizeof(IcpState)));
     WCU_CHECK(cudaMalloc((void **) &d_acc, sizeof(Acc128) * kAccSlots * kMaxAcc));
@@ -259,10 +264,9 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     IterArgs ia;
     ia.cur = src.d_sorted;
     ia.n_src = (int) n_src;
-    ia.nodes = tgt.d_nodes;
+    ia.ix = tgt.index();
     ia.tgt = tgt.cloud.d_sorted;
     ia.nrm = tgt.d_nrm_sorted;
-    ia.root = tgt.d_root;
     ia.nn_pos = d_nn_pos;
     ia.nn_idx = d_nn_idx;
     ia.nn_d2 = d_nn_d2;
@@ -288,10 +292,10 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         }
         if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
             reduce_kernel<WAVECU_EST_POINT_TO_PLANE><<<grid_red, kReduceThreads, 0, stream>>>(ia);
-            solve_kernel<WAVECU_EST_POINT_TO_PLANE><<<1, 32, 0, stream>>>(so);
+            solve_kernel<WAVECU_EST_POINT_TO_PLANE><<<1, 64, 0, stream>>>(so);
         } else {
             reduce_kernel<WAVECU_EST_SVD><<<grid_red, kReduceThreads, 0, stream>>>(ia);
-            solve_kernel<WAVECU_EST_SVD><<<1, 32, 0, stream>>>(so);
+            solve_kernel<WAVECU_EST_SVD><<<1, 64, 0, stream>>>(so);
         }
         if (profiling) {
             it_ev.push_back(next_event());

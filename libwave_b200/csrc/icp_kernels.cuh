@@ -17,7 +17,13 @@
 
 namespace wavecu {
 
-constexpr int kIterThreads = 128;       // correspondence kernel: one query per thread
+#ifndef WCU_MINBLOCKS
+#define WCU_MINBLOCKS 8
+#endif
+#ifndef WCU_ITER_THREADS
+#define WCU_ITER_THREADS 128
+#endif
+constexpr int kIterThreads = WCU_ITER_THREADS;  // correspondence kernel: one query per thread
 constexpr int kReduceThreads = 256;     // reduction kernel
 constexpr int kReducePerThread = 8;
 constexpr int kReduceWarps = kReduceThreads / 32;
@@ -25,9 +31,8 @@ constexpr int kReduceWarps = kReduceThreads / 32;
 struct IterArgs {
     float4 *cur;                 // working source cloud, Morton order, w = original index
     int n_src;
-    const TNode *nodes;
-    const TreeRoot *root;
-    const float4 *tgt;
+    NnIndex ix;                  // target search structure
+    const float4 *tgt;           // == ix.pts
     const float4 *nrm;           // sorted target normals (point-to-plane) or nullptr
     int *nn_pos;                 // sorted position of the match (-1: none) - warm start + gathers
     int *nn_idx;                 // original target index of the match (-1: none)
@@ -76,7 +81,7 @@ __device__ __forceinline__ void warp_reduce_transpose(long long (&v)[NV], int la
 
 // Correspondence kernel (A.3.2 + A.3.1): cur <- T_inc (x) cur in place, then the exact 1-NN of the
 // moved point within the max-correspondence distance, warm-started from the previous match.
-__global__ void __launch_bounds__(kIterThreads, 8) correspond_kernel(IterArgs a) {
+__global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) correspond_kernel(IterArgs a) {
     if (a.st->done) return;
     __shared__ float sT[12];
     if (threadIdx.x < 12) sT[threadIdx.x] = a.st->T_inc[threadIdx.x];
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(kIterThreads, 8) correspond_kernel(IterArgs a)
             best_pos = warm;
         }
     }
-    nn_search(x, y, z, a.nodes, a.root, a.tgt, best, best_idx, best_pos);
+    nn_search(x, y, z, a.ix, best, best_idx, best_pos);
     a.nn_pos[s] = best_pos;
     a.nn_idx[s] = best_pos >= 0 ? best_idx : -1;
     a.nn_d2[s] = best;
@@ -321,25 +326,31 @@ __device__ inline bool solve6(const double A_in[36], const double b_in[6], doubl
 }
 
 template <int EST>
-__global__ void solve_kernel(SolveArgs a) {
+__global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
     constexpr int NV = EstTraits<EST>::NV;
-    if (threadIdx.x != 0 || a.st->done) return;
-    IcpState &st = *a.st;
-    const MatchConsts &mc = *a.mc;
-
-    __int128 tot[NV + 1];
-    for (int i = 0; i <= NV; ++i) {
+    if (a.st->done) return;
+    // threads 0..NV: one accumulator each, summed over the slots (and cleared for the next
+    // iteration); then thread 0 runs the estimator
+    __shared__ unsigned long long s_lo[NV + 1];
+    __shared__ long long s_hi[NV + 1];
+    if (threadIdx.x <= NV) {
         __int128 t = 0;
+#pragma unroll 4
         for (int sl = 0; sl < kAccSlots; ++sl) {
-            Acc128 &c = a.acc[sl * kMaxAcc + i];
+            Acc128 &c = a.acc[sl * kMaxAcc + threadIdx.x];
             t += ((__int128) c.hi << 64) + (__int128) c.lo;
             c.lo = 0;
             c.hi = 0;
         }
-        tot[i] = t;
+        s_lo[threadIdx.x] = (unsigned long long) t;
+        s_hi[threadIdx.x] = (long long) (t >> 64);
     }
-    auto val = [&](int i, int k) { return acc_to_double((unsigned long long) tot[i], (long long) (tot[i] >> 64), k); };
-    const long long n = (long long) tot[NV];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    IcpState &st = *a.st;
+    const MatchConsts &mc = *a.mc;
+    auto val = [&](int i, int k) { return acc_to_double(s_lo[i], s_hi[i], k); };
+    const long long n = (long long) s_lo[NV];
     if (n < 3) {  // min_number_correspondences_
         st.n_corr = (int) n;
         st.converged = 0;

@@ -38,45 +38,45 @@ __global__ void __launch_bounds__(kBuildThreads) bbox_kernel(const float4 *__res
             hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
         }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if ((threadIdx.x & 31) == 0) {
-        if (cnt) atomicAdd(&bbox[6], cnt);
+    __shared__ float s_lo[kBuildThreads / 32][3], s_hi[kBuildThreads / 32][3];
+    __shared__ unsigned s_cnt[kBuildThreads / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            if (lo[d] <= hi[d]) {
-                atomicMin(&bbox[d], float_to_ordered(lo[d]));
-                atomicMax(&bbox[3 + d], float_to_ordered(hi[d]));
-            }
+            s_lo[warp][d] = lo[d];
+            s_hi[warp][d] = hi[d];
         }
+        s_cnt[warp] = cnt;
     }
-}
-
-__device__ __forceinline__ unsigned long long expand21(unsigned long long v) {
-    v &= 0x1fffffull;
-    v = (v | v << 32) & 0x1f00000000ffffull;
-    v = (v | v << 16) & 0x1f0000ff0000ffull;
-    v = (v | v << 8) & 0x100f00f00f00f00full;
-    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
-    v = (v | v << 2) & 0x1249249249249249ull;
-    return v;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int d = threadIdx.x;
+        float l = s_lo[0][d], h = s_hi[0][d];
+        for (int w = 1; w < kBuildThreads / 32; ++w) {
+            l = fminf(l, s_lo[w][d]);
+            h = fmaxf(h, s_hi[w][d]);
+        }
+        if (l <= h) {
+            atomicMin(&bbox[d], float_to_ordered(l));
+            atomicMax(&bbox[3 + d], float_to_ordered(h));
+        }
+    } else if (threadIdx.x == 3) {
+        unsigned c = 0;
+        for (int w = 0; w < kBuildThreads / 32; ++w) c += s_cnt[w];
+        if (c) atomicAdd(&bbox[6], c);
+    }
 }
 
 __global__ void __launch_bounds__(kBuildThreads) morton_kernel(const float4 *__restrict__ pts, size_t n,
-                                                               const unsigned *__restrict__ bbox,
+                                                               const unsigned *__restrict__ bbox, int bits,
                                                                unsigned long long *keys, unsigned *vals) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float lx = ordered_to_float(bbox[0]), ly = ordered_to_float(bbox[1]), lz = ordered_to_float(bbox[2]);
-    const float ext = fmaxf(fmaxf(ordered_to_float(bbox[3]) - lx, ordered_to_float(bbox[4]) - ly),
-                            ordered_to_float(bbox[5]) - lz);
-    const float scale = (ext > 0.0f && isfinite(ext)) ? 2097151.0f / ext : 0.0f;
+    const QuantParams qp = make_quant(bbox, bits);
     const float4 p = pts[i];
-    unsigned long long key = ~0ull;  // non-finite points sort to the end and become pads
-    if (finite3(p.x, p.y, p.z)) {
-        const unsigned qx = (unsigned) fminf(fmaxf((p.x - lx) * scale, 0.0f), 2097151.0f);
-        const unsigned qy = (unsigned) fminf(fmaxf((p.y - ly) * scale, 0.0f), 2097151.0f);
-        const unsigned qz = (unsigned) fminf(fmaxf((p.z - lz) * scale, 0.0f), 2097151.0f);
-        key = expand21(qx) | (expand21(qy) << 1) | (expand21(qz) << 2);
-    }
+    unsigned long long key = 1ull << (3 * bits);  // non-finite points sort to the end and become pads
+    if (finite3(p.x, p.y, p.z)) key = morton_code(qp, p.x, p.y, p.z);
     keys[i] = key;
     vals[i] = (unsigned) i;
 }
@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(kBuildThreads) morton_kernel(const float4 *__r
 __global__ void __launch_bounds__(kBuildThreads) gather_kernel(const float4 *__restrict__ pts,
                                                                const unsigned long long *__restrict__ keys,
                                                                const unsigned *__restrict__ vals, size_t n,
-                                                               size_t n_pad, float4 *out,
+                                                               size_t n_pad, int bits, float4 *out,
                                                                const float4 *__restrict__ extra_in, float4 *extra_out) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     float4 o = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7fffffff));
     float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < n && keys[i] != ~0ull) {
+    if (i < n && (keys[i] >> (3 * bits)) == 0ull) {
         const unsigned src = vals[i];
         const float4 p = pts[src];
         o = make_float4(p.x, p.y, p.z, __int_as_float((int) src));
@@ -131,10 +131,9 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
     float lox = p.x, loy = p.y, loz = p.z, hix = p.x, hiy = p.y, hiz = p.z;
     int link = make_leaf_link(i, 1);
     for (;;) {
-        const int cnt = r - l + 1;
         if (l == 0 && r == n - 1) {
             root->lo = make_float4(lox, loy, loz, __int_as_float(link));
-            root->hi = make_float4(hix, hiy, hiz, __int_as_float(cnt));
+            root->hi = make_float4(hix, hiy, hiz, __int_as_float(r - l + 1));
             return;
         }
         bool parent_right;  // parent is gap r: this node is its left child
@@ -145,10 +144,10 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
         TNode *nd = nodes + par;
         if (parent_right) {
             nd->lo0 = make_float4(lox, loy, loz, __int_as_float(link));
-            nd->hi0 = make_float4(hix, hiy, hiz, __int_as_float(cnt));
+            nd->hi0 = make_float4(hix, hiy, hiz, 0.0f);
         } else {
             nd->lo1 = make_float4(lox, loy, loz, __int_as_float(link));
-            nd->hi1 = make_float4(hix, hiy, hiz, __int_as_float(cnt));
+            nd->hi1 = make_float4(hix, hiy, hiz, 0.0f);
         }
         __threadfence();
         const int prev = atomicExch(&other[par], parent_right ? l : r);
@@ -236,22 +235,22 @@ int MortonCloud::sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_e
     bbox_init_kernel<<<1, 32, 0, stream>>>(d_bbox);
     ++launches;
     if (n) {
-        const int grid = (int) std::min<size_t>((n + kBuildThreads - 1) / kBuildThreads, 148 * 8);
+        const int grid = (int) std::min<size_t>((n + kBuildThreads - 1) / kBuildThreads, 148 * 4);
         bbox_kernel<<<grid, kBuildThreads, 0, stream>>>(d_raw, n, d_bbox);
         morton_kernel<<<(unsigned) ((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, stream>>>(
-            d_raw, n, d_bbox, d_keys, d_vals);
+            d_raw, n, d_bbox, key_bits, d_keys, d_vals);
         launches += 2;
         cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys_alt);
         cub::DoubleBuffer<unsigned> vb(d_vals, d_vals_alt);
         size_t need = tmp_bytes;
-        WCU_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, need, kb, vb, (int) n, 0, 64, stream));
-        launches += 8;  // histogram + onesweep passes (approximate; CUB-internal)
+        WCU_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, need, kb, vb, (int) n, 0, 3 * key_bits + 1, stream));
+        launches += 2 + (3 * key_bits + 8) / 8;  // histogram + scan + onesweep passes (CUB-internal)
         if (kb.Current() != d_keys) std::swap(d_keys, d_keys_alt);
         if (vb.Current() != d_vals) std::swap(d_vals, d_vals_alt);
     }
     if (n_sorted_pad) {
         gather_kernel<<<(unsigned) ((n_sorted_pad + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, stream>>>(
-            d_raw, d_keys, d_vals, n, n_sorted_pad, d_sorted, d_extra_in, d_extra_out);
+            d_raw, d_keys, d_vals, n, n_sorted_pad, key_bits, d_sorted, d_extra_in, d_extra_out);
         ++launches;
     }
     WCU_CHECK(cudaGetLastError());

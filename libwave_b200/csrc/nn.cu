@@ -26,9 +26,7 @@ constexpr int kNnThreads = 128;
 
 // queries in Morton order (w = original index); results written in original query order
 __global__ void __launch_bounds__(kNnThreads) nn_kernel(const float4 *__restrict__ q_sorted, int nq,
-                                                         const TNode *__restrict__ nodes,
-                                                         const TreeRoot *__restrict__ root,
-                                                         const float4 *__restrict__ tgt, float thr, int *out_idx,
+                                                         NnIndex ix, float thr, int *out_idx,
                                                          float *out_d2) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nq) return;
@@ -37,7 +35,7 @@ __global__ void __launch_bounds__(kNnThreads) nn_kernel(const float4 *__restrict
     if (orig == 0x7fffffff) return;  // pad (non-finite query): left at -1 / inf by the caller's fill
     float best = thr;
     int best_idx = 0x7fffffff, best_pos = -1;
-    nn_search(q.x, q.y, q.z, nodes, root, tgt, best, best_idx, best_pos);
+    nn_search(q.x, q.y, q.z, ix, best, best_idx, best_pos);
     out_idx[orig] = best_pos >= 0 ? best_idx : -1;
     out_d2[orig] = best_pos >= 0 ? best : INFINITY;
 }
@@ -101,7 +99,7 @@ struct NnHandle {
         if (elapsed_ms) WCU_CHECK(cudaEventRecord(e0, stream));
         for (int r = 0; r < repeats; ++r)
             nn_kernel<<<(unsigned) ((nq + kNnThreads - 1) / kNnThreads), kNnThreads, 0, stream>>>(
-                q.d_sorted, (int) nq, tgt.d_nodes, tgt.d_root, tgt.cloud.d_sorted, thr, o_idx, o_d2);
+                q.d_sorted, (int) nq, tgt.index(), thr, o_idx, o_d2);
         if (elapsed_ms) WCU_CHECK(cudaEventRecord(e1, stream));
         WCU_CHECK(cudaGetLastError());
         if (!out_on_device) {
@@ -154,6 +152,7 @@ int wavecu_nn_create(int device, void *stream, wavecu_nn **out) {
         WCU_CHECK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
         h.own_stream = true;
     }
+    h.q.key_bits = 10;
     h.tgt.cloud.device = h.q.device = device;
     h.tgt.cloud.stream = h.q.stream = h.stream;
     WCU_CHECK(cudaEventCreate(&h.e0));

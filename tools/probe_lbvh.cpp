@@ -46,6 +46,20 @@ int main(int argc, char **argv) {
             if (nd.left < 0) { ++nl; for (int i = nd.b; i < nd.e; ++i) { const float *c = &tgt[perm[i]].x; float dx = q[0] - c[0], dy = q[1] - c[1], dz = q[2] - c[2]; float d = dx * dx + dy * dy + dz * dz; ++np; if (d < best) best = d; } }
             else { ++nn; float d0 = bdist(nodes[nd.left], q), d1 = bdist(nodes[nd.right], q); if (d0 <= d1) { if (d1 <= best) { stack[sp] = nd.right; sd[sp++] = d1; } if (d0 <= best) { stack[sp] = nd.left; sd[sp++] = d0; } } else { if (d0 <= best) { stack[sp] = nd.left; sd[sp++] = d0; } if (d1 <= best) { stack[sp] = nd.right; sd[sp++] = d1; } } } }
         tot_leaf += nl; tot_node += nn; tot_pts += np; lv.push_back(nl); }
+    // wide traversal: node = up to W children obtained by expanding internal children (largest box first) 
+    for (int W : {2, 4, 8}) {
+        double wv = 0, wb = 0, wl = 0, wp = 0, wpush = 0; size_t cntq = 0;
+        for (size_t qi = 0; qi < nq; qi += stride) { const float *q = &qry[qi].x; float best = 9.f; ++cntq;
+            struct E { int ni; float d; }; std::vector<E> st; st.push_back({0, 0.f});
+            while (!st.empty()) { E e = st.back(); st.pop_back(); if (e.d > best) continue; const Node &nd = nodes[e.ni];
+                if (nd.left < 0) { ++wl; for (int i = nd.b; i < nd.e; ++i) { const float *c = &tgt[perm[i]].x; float dx = q[0] - c[0], dy = q[1] - c[1], dz = q[2] - c[2]; float d = dx * dx + dy * dy + dz * dz; ++wp; if (d < best) best = d; } continue; }
+                // gather children of wide node
+                std::vector<int> ch = {nd.left, nd.right};
+                while ((int) ch.size() < W) { int bi = -1; int bc = 0; for (size_t k = 0; k < ch.size(); ++k) { const Node &c = nodes[ch[k]]; if (c.left >= 0 && c.e - c.b > bc) { bc = c.e - c.b; bi = k; } } if (bi < 0) break; int c = ch[bi]; ch[bi] = nodes[c].left; ch.push_back(nodes[c].right); }
+                ++wv; wb += ch.size(); std::vector<E> hits; for (int c : ch) { float d = bdist(nodes[c], q); if (d <= best) hits.push_back({c, d}); }
+                std::sort(hits.begin(), hits.end(), [](const E &a, const E &b) { return a.d > b.d; }); wpush += hits.size() > 0 ? hits.size() - 1 : 0; for (auto &h : hits) st.push_back(h); } }
+        printf("  W=%d: visits %.1f boxes %.1f leaves %.1f pts %.1f pushes %.1f  cost~%.0f\n", W, wv / cntq, wb / cntq, wl / cntq, wp / cntq, wpush / cntq, (wv * 12 + wb * 14 + wl * 10 + wp * 12 + wpush * 8) / cntq);
+    }
     std::sort(lv.begin(), lv.end()); size_t m = lv.size();
     printf("lbvh split %d L %d: nodes %zu leaves %zu (avg %.1f pts) | leaves/query mean %.1f p50 %d p90 %d p99 %d | internal visits %.1f | pts %.1f\n", splitmode, L, nodes.size(), nleaf, (double) leafpts / nleaf, tot_leaf / m, lv[m / 2], lv[m * 9 / 10], lv[m * 99 / 100], tot_node / m, tot_pts / m);
 }
