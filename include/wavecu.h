@@ -140,6 +140,12 @@ int wavecu_nn_search(wavecu_nn *h, const float *q_xyzw, size_t nq, double max_di
 int wavecu_nn_search_device(wavecu_nn *h, const void *d_q_xyzw, size_t nq, double max_dist, void *d_idx,
                             void *d_dist2, int repeats, float *elapsed_ms);
 
+/* pcl::VoxelGrid<pcl::PointXYZ>::filter (src/icp.cpp:81-90,106-113; src/gicp.cpp:39-40,49-50):
+ * one centroid per occupied voxel in ascending voxel index; out_xyzw needs room for n points.
+ * *filtered = 0 when the grid would overflow int32 and the input is passed through unchanged. */
+int wavecu_voxel_grid(int device, const float *xyzw, size_t n, float leaf, float *out_xyzw, size_t *n_out,
+                      int *filtered);
+
 const char *wavecu_last_error(void);
 int wavecu_device_count(void);
 

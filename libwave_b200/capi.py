@@ -61,6 +61,7 @@ SIGNATURES = {
     "wavecu_nn_set_target": (C.c_int, [_vp, _fp, _sz]),
     "wavecu_nn_search": (C.c_int, [_vp, _fp, _sz, C.c_double, _ip, _fp]),
     "wavecu_nn_search_device": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, C.c_int, _fp]),
+    "wavecu_voxel_grid": (C.c_int, [C.c_int, _fp, _sz, C.c_float, _fp, _szp, _ip]),
     "wavecu_last_error": (C.c_char_p, []),
     "wavecu_device_count": (C.c_int, []),
 }

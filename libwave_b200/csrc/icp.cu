@@ -12,6 +12,8 @@
 #include "../../include/wavecu.h"
 #include "icp_kernels.cuh"
 #include "index.cuh"
+#include "info_kernels.cuh"
+#include "voxel.cuh"
 
 namespace wavecu {
 
@@ -150,6 +152,17 @@ struct IcpHandle {
     IcpState last;
     std::vector<TraceRow> trace;
 
+    // voxel-filtered / multiscale path: the clouds as the caller gave them
+    VoxelWork vox;
+    float4 *d_orig_src = nullptr, *d_orig_tgt = nullptr;
+    size_t orig_src_cap = 0, orig_tgt_cap = 0, n_orig_src = 0, n_orig_tgt = 0;
+    bool src_is_user = true, tgt_is_user = true;   // working clouds still hold the caller's data
+    bool have_orig_src = false, have_orig_tgt = false;
+    MatchConsts last_mc{};
+    int *d_pos2 = nullptr;  // estimateLUMold correspondences
+    size_t pos2_cap = 0;
+    Acc128 *h_acc = nullptr;  // pinned mirror of the accumulators
+
     // profiling
     bool profiling = false;
     wavecu_stats stats{};
@@ -158,6 +171,12 @@ struct IcpHandle {
     int init();
     int ensure_iter_buffers(size_t n_src_pad, int max_iter);
     int align(double *T_out, int *converged, int *iterations, int *state);
+    int stash_originals();
+    int restore_originals();
+    int load_level(float leaf, const double *running);
+    int match(double *T_out, int *converged, int *iterations);
+    int info(int method, double *info_out);
+    int read_acc(int n_values, __int128 *out);
     void release();
 };
 
@@ -178,6 +197,9 @@ int IcpHandle::init() {
     WCU_CHECK(cudaMalloc((void **) &d_acc, sizeof(Acc128) * kAccSlots * kMaxAcc));
     WCU_CHECK(cudaHostAlloc((void **) &h_done, sizeof(int) * kDepth, cudaHostAllocDefault));
     WCU_CHECK(cudaHostAlloc((void **) &h_st, sizeof(IcpState), cudaHostAllocDefault));
+    WCU_CHECK(cudaHostAlloc((void **) &h_acc, sizeof(Acc128) * kAccSlots * kMaxAcc, cudaHostAllocDefault));
+    vox.device = device;
+    vox.stream = stream;
     for (int i = 0; i < kDepth; ++i) WCU_CHECK(cudaEventCreateWithFlags(&ev_ring[i], cudaEventDisableTiming));
     return WAVECU_OK;
 }
@@ -314,6 +336,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     }
     if (profiling) WCU_CHECK(cudaEventRecord(e_end, stream));
     WCU_CHECK(cudaMemcpyAsync(h_st, d_st, sizeof(IcpState), cudaMemcpyDeviceToHost, stream));
+    WCU_CHECK(cudaMemcpyAsync(&last_mc, d_mc, sizeof(MatchConsts), cudaMemcpyDeviceToHost, stream));
     WCU_CHECK(cudaStreamSynchronize(stream));
     WCU_CHECK(cudaGetLastError());
     last = *h_st;
@@ -353,6 +376,319 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     return WAVECU_OK;
 }
 
+// ---- ICPMatcher::match(), src/icp.cpp:75-133 -------------------------------------------------------
+int IcpHandle::stash_originals() {
+    if (src_is_user) {
+        if (src.n > orig_src_cap) {
+            if (d_orig_src) WCU_CHECK(cudaFree(d_orig_src));
+            d_orig_src = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &d_orig_src, (src.n + 64) * sizeof(float4)));
+            orig_src_cap = src.n + 64;
+        }
+        if (src.n) WCU_CHECK(cudaMemcpyAsync(d_orig_src, src.d_raw, src.n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        n_orig_src = src.n;
+        have_orig_src = true;
+        src_is_user = false;
+    }
+    if (tgt_is_user) {
+        if (tgt.cloud.n > orig_tgt_cap) {
+            if (d_orig_tgt) WCU_CHECK(cudaFree(d_orig_tgt));
+            d_orig_tgt = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &d_orig_tgt, (tgt.cloud.n + 64) * sizeof(float4)));
+            orig_tgt_cap = tgt.cloud.n + 64;
+        }
+        if (tgt.cloud.n)
+            WCU_CHECK(cudaMemcpyAsync(d_orig_tgt, tgt.cloud.d_raw, tgt.cloud.n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        n_orig_tgt = tgt.cloud.n;
+        have_orig_tgt = true;
+        tgt_is_user = false;
+    }
+    return WAVECU_OK;
+}
+
+int IcpHandle::restore_originals() {
+    if (!src_is_user && have_orig_src) {
+        int rc = src.upload((const float *) d_orig_src, n_orig_src, true);
+        if (rc) return rc;
+        src_is_user = true;
+    }
+    if (!tgt_is_user && have_orig_tgt) {
+        int rc = tgt.set_points((const float *) d_orig_tgt, n_orig_tgt, true);
+        if (rc) return rc;
+        tgt_is_user = true;
+    }
+    return WAVECU_OK;
+}
+
+// working clouds <- VoxelGrid(leaf) of the caller's clouds; the source additionally moved by the
+// running transform (pcl::transformPointCloud with an Affine3d, src/icp.cpp:84-86)
+int IcpHandle::load_level(float leaf, const double *running) {
+    int rc = src.reserve(std::max<size_t>(n_orig_src, 1), 0);
+    if (rc) return rc;
+    size_t n_out = 0;
+    rc = vox.filter(d_orig_src, n_orig_src, leaf, src.d_raw, &n_out, nullptr);
+    if (rc) return rc;
+    src.n = n_out;
+    if (running) {
+        rc = affine3d_inplace(src.d_raw, n_out, running, stream);
+        if (rc) return rc;
+    }
+    rc = tgt.cloud.reserve(std::max<size_t>(n_orig_tgt, 1), 0);
+    if (rc) return rc;
+    rc = vox.filter(d_orig_tgt, n_orig_tgt, leaf, tgt.cloud.d_raw, &n_out, nullptr);
+    if (rc) return rc;
+    tgt.cloud.n = n_out;
+    tgt.nrm_n = 0;
+    tgt.dirty = true;
+    return WAVECU_OK;
+}
+
+int IcpHandle::match(double *T_out, int *converged, int *iterations) {
+    WCU_CHECK(cudaSetDevice(device));
+    if (converged) *converged = 0;
+    if (iterations) *iterations = 0;
+    if (!(prm.res > 0)) {
+        // full-resolution branch, src/icp.cpp:123-131
+        int rc = restore_originals();
+        if (rc) return rc;
+        return align(T_out, converged, iterations, nullptr);
+    }
+    if (prm.estimator != WAVECU_EST_SVD) {
+        set_last_error("the point-to-plane estimator needs per-point target normals: use res <= 0");
+        return WAVECU_ERR_STATE;
+    }
+    int rc = stash_originals();
+    if (rc) return rc;
+    const double user_max_corr = prm.max_corr;
+    int total_iters = 0, conv = 0;
+    double T[16];
+    if (prm.multiscale_steps > 0) {
+        double running[16];
+        for (int i = 0; i < 16; ++i) running[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        for (int i = prm.multiscale_steps; i >= 0; --i) {
+            const float leaf_size = std::pow(2, i) * prm.res;
+            rc = load_level(leaf_size, running);
+            if (rc) break;
+            prm.max_corr = std::pow(2, i) * user_max_corr;
+            int it = 0;
+            rc = align(T, &conv, &it, nullptr);
+            if (rc) break;
+            total_iters += it;
+            if (!conv) break;  // any level failing to converge fails the match, src/icp.cpp:96-98
+            // running = final.cast<double>() * running (Eigen column order)
+            double out[16];
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 4; ++c) {
+                    double acc = T[4 * r + 0] * running[0 * 4 + c];
+                    acc = T[4 * r + 1] * running[1 * 4 + c] + acc;
+                    acc = T[4 * r + 2] * running[2 * 4 + c] + acc;
+                    acc = T[4 * r + 3] * running[3 * 4 + c] + acc;
+                    out[4 * r + c] = acc;
+                }
+            std::memcpy(running, out, sizeof out);
+        }
+        prm.max_corr = user_max_corr;
+        if (rc) return rc;
+        if (conv) std::memcpy(T, running, sizeof running);
+    } else {
+        rc = load_level(prm.res, nullptr);
+        if (rc) return rc;
+        rc = align(T, &conv, &total_iters, nullptr);
+        if (rc) return rc;
+    }
+    if (T_out) std::memcpy(T_out, T, sizeof T);
+    if (converged) *converged = conv;
+    if (iterations) *iterations = total_iters;
+    return WAVECU_OK;
+}
+
+// ---- information matrices ---------------------------------------------------------------------------
+int IcpHandle::read_acc(int n_values, __int128 *out) {
+    WCU_CHECK(cudaMemcpyAsync(h_acc, d_acc, sizeof(Acc128) * kAccSlots * kMaxAcc, cudaMemcpyDeviceToHost, stream));
+    WCU_CHECK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < n_values; ++i) {
+        __int128 t = 0;
+        for (int sl = 0; sl < kAccSlots; ++sl) {
+            const Acc128 &c = h_acc[sl * kMaxAcc + i];
+            t += ((__int128) c.hi << 64) + (__int128) c.lo;
+        }
+        out[i] = t;
+    }
+    return WAVECU_OK;
+}
+
+namespace {
+
+double fix_to_double(__int128 v, int k) {
+    const long long hi = (long long) (v >> 64);
+    const unsigned long long lo = (unsigned long long) v;
+    return std::ldexp((double) hi, 64 - k) + std::ldexp((double) lo, -k);
+}
+
+// N x N solve by Gaussian elimination with partial pivoting (fixed order), used column by column
+// for MM.inverse() - the information estimators only
+bool solve6_host(const double *A_in, const double *b_in, double *x) {
+    double A[6][7];
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) A[i][j] = A_in[6 * i + j];
+        A[i][6] = b_in[i];
+    }
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        double best = std::fabs(A[c][c]);
+        for (int r = c + 1; r < 6; ++r)
+            if (std::fabs(A[r][c]) > best) {
+                best = std::fabs(A[r][c]);
+                piv = r;
+            }
+        if (best == 0.0 || !std::isfinite(best)) return false;
+        if (piv != c)
+            for (int j = 0; j <= 6; ++j) std::swap(A[c][j], A[piv][j]);
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = A[r][c] / A[c][c];
+            for (int j = c; j <= 6; ++j) A[r][j] = A[r][j] - f * A[c][j];
+        }
+    }
+    for (int r = 5; r >= 0; --r) {
+        double s = A[r][6];
+        for (int j = r + 1; j < 6; ++j) s = s - A[r][j] * x[j];
+        x[r] = s / A[r][r];
+    }
+    return true;
+}
+
+}  // namespace
+
+int IcpHandle::info(int method, double *info_out) {
+    WCU_CHECK(cudaSetDevice(device));
+    if (!have_result) {
+        set_last_error("estimateInfo needs a match() result");
+        return WAVECU_ERR_STATE;
+    }
+    if (method == WAVECU_INFO_CENSI) {
+        set_last_error("the Censi estimator is not built yet (its result is always overwritten by LUMold in the "
+                       "reference's estimateInfo fall-through, src/icp.cpp:135-142)");
+        return WAVECU_ERR_STATE;
+    }
+    // estimateLUM only acts if icp.hasConverged() (icp_pcl_functions.cpp:190): otherwise keep the
+    // caller's matrix untouched - signalled by returning the identity the base class starts from
+    const size_t ns = result_n_src;
+    const int *pos = d_nn_pos;
+    if (method == WAVECU_INFO_LUM && !last.converged) {
+        for (int i = 0; i < 36; ++i) info_out[i] = (i % 7 == 0) ? 1.0 : 0.0;
+        return WAVECU_OK;
+    }
+    if (ns == 0) {
+        for (int i = 0; i < 36; ++i) info_out[i] = std::nan("");
+        return WAVECU_OK;
+    }
+    if (method == WAVECU_INFO_LUMOLD) {
+        if (ns > pos2_cap) {
+            if (d_pos2) WCU_CHECK(cudaFree(d_pos2));
+            d_pos2 = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &d_pos2, (ns + 64) * sizeof(int)));
+            pos2_cap = ns + 64;
+        }
+        LumOldArgs oa;
+        oa.cur = src.d_sorted;
+        oa.raw = src.d_raw;
+        oa.n_src = (int) ns;
+        oa.ix = tgt.index();
+        oa.warm = d_nn_pos;
+        oa.st = d_st;
+        const double max2 = prm.max_corr * prm.max_corr;
+        float f = (max2 >= (double) FLT_MAX) ? FLT_MAX : (float) max2;
+        if (!((double) f < max2)) f = std::nextafterf(f, -INFINITY);  // d2 < max^2, icp_pcl_functions.cpp:82
+        oa.thr_strict = f;
+        oa.pos_out = d_pos2;
+        lumold_corr_kernel<<<(unsigned) ((ns + kIterThreads - 1) / kIterThreads), kIterThreads, 0, stream>>>(oa);
+        pos = d_pos2;
+    }
+    LumArgs la;
+    la.cur = src.d_sorted;
+    la.raw = src.d_raw;
+    la.n_src = (int) ns;
+    la.tgt = tgt.cloud.d_sorted;
+    la.pos = pos;
+    la.st = d_st;
+    la.acc = d_acc;
+    const int k = last_mc.k_quad - 2, k_ss = last_mc.k_quad - 4;
+    la.scale = std::ldexp(1.0, k);
+    la.scale_ss = std::ldexp(1.0, k_ss);
+    for (int i = 0; i < 6; ++i) la.D[i] = 0;
+    const unsigned grid = (unsigned) std::max<size_t>(
+        1, (ns + kReduceThreads * kReducePerThread - 1) / (kReduceThreads * kReducePerThread));
+    zero_acc_kernel<<<1, 256, 0, stream>>>(d_acc);
+    lum_kernel<0><<<grid, kReduceThreads, 0, stream>>>(la);
+    __int128 tot[17];
+    int rc = read_acc(17, tot);
+    if (rc) return rc;
+    const long long numCorr = (long long) tot[16];
+    double v[15];
+    for (int i = 0; i < 15; ++i) v[i] = fix_to_double(tot[i], k);
+    double MM[36], MZ[6];
+    for (int i = 0; i < 36; ++i) MM[i] = 0;
+    auto M = [&](int r, int c) -> double & { return MM[6 * r + c]; };
+    M(0, 4) = -v[1];
+    M(0, 5) = v[2];
+    M(1, 3) = -v[2];
+    M(1, 4) = v[0];
+    M(2, 3) = v[1];
+    M(2, 5) = -v[0];
+    M(3, 4) = -v[3];
+    M(3, 5) = -v[4];
+    M(4, 5) = -v[5];
+    M(3, 3) = v[6];
+    M(4, 4) = v[7];
+    M(5, 5) = v[8];
+    for (int i = 0; i < 6; ++i) MZ[i] = v[9 + i];
+    M(0, 0) = M(1, 1) = M(2, 2) = static_cast<float>(numCorr);
+    M(4, 0) = M(0, 4);
+    M(5, 0) = M(0, 5);
+    M(3, 1) = M(1, 3);
+    M(4, 1) = M(1, 4);
+    M(3, 2) = M(2, 3);
+    M(5, 2) = M(2, 5);
+    M(4, 3) = M(3, 4);
+    M(5, 3) = M(3, 5);
+    M(5, 4) = M(4, 5);
+    // D = MM.inverse() * MZ
+    double inv[36];
+    bool ok = true;
+    for (int c = 0; c < 6 && ok; ++c) {
+        double e[6], x[6];
+        for (int i = 0; i < 6; ++i) e[i] = (i == c) ? 1.0 : 0.0;
+        ok = solve6_host(MM, e, x);
+        for (int i = 0; i < 6; ++i) inv[6 * i + c] = x[i];
+    }
+    for (int r = 0; r < 6; ++r) {
+        double sum = 0;
+        for (int c = 0; c < 6; ++c) sum += inv[6 * r + c] * MZ[c];
+        la.D[r] = ok ? sum : std::nan("");
+    }
+    float ss;
+    if (ok) {
+        zero_acc_kernel<<<1, 256, 0, stream>>>(d_acc);
+        lum_kernel<1><<<grid, kReduceThreads, 0, stream>>>(la);
+        rc = read_acc(2, tot);
+        if (rc) return rc;
+        ss = (tot[1] != 0) ? std::nanf("") : static_cast<float>(fix_to_double(tot[0], k_ss));
+    } else {
+        ss = std::nanf("");
+    }
+    zero_acc_kernel<<<1, 256, 0, stream>>>(d_acc);  // leave the accumulators clean for the next align
+    WCU_CHECK(cudaGetLastError());
+    if (ss < 0.0000000000001 || !std::isfinite(ss)) {
+        // "Covariance matrix calculation was unsuccessful": estimateLUM returns the identity;
+        // estimateLUMold falls through and overwrites it with MM / ss (icp_pcl_functions.cpp:170-178)
+        for (int i = 0; i < 36; ++i) info_out[i] = (i % 7 == 0) ? 1.0 : 0.0;
+        if (method == WAVECU_INFO_LUM) return WAVECU_OK;
+    }
+    const float rec = 1.0f / ss;
+    for (int i = 0; i < 36; ++i) info_out[i] = MM[i] * rec;
+    return WAVECU_OK;
+}
+
 void IcpHandle::release() {
     cudaSetDevice(device);
     src.release();
@@ -360,6 +696,10 @@ void IcpHandle::release() {
     for (void *p : {(void *) d_nn_pos, (void *) d_nn_idx, (void *) d_nn_d2, (void *) d_out_idx, (void *) d_out_d2,
                     (void *) d_aligned, (void *) d_mc, (void *) d_st, (void *) d_acc, (void *) d_trace})
         if (p) cudaFree(p);
+    vox.release();
+    for (void *p : {(void *) d_orig_src, (void *) d_orig_tgt, (void *) d_pos2})
+        if (p) cudaFree(p);
+    if (h_acc) cudaFreeHost(h_acc);
     if (h_done) cudaFreeHost(h_done);
     if (h_st) cudaFreeHost(h_st);
     for (auto &e : ev_ring)
@@ -430,23 +770,31 @@ int wavecu_icp_set_params(wavecu_icp *w, const wavecu_icp_params *params) {
 
 int wavecu_icp_set_source(wavecu_icp *w, const float *xyzw, size_t n) {
     if (!w || (!xyzw && n)) return WAVECU_ERR_ARG;
+    w->h.src_is_user = true;
+    w->h.have_orig_src = false;
     w->h.src_dirty = true;
     w->h.have_result = false;
     return w->h.src.upload(xyzw, n, false);
 }
 int wavecu_icp_set_source_device(wavecu_icp *w, const void *d, size_t n) {
     if (!w || (!d && n)) return WAVECU_ERR_ARG;
+    w->h.src_is_user = true;
+    w->h.have_orig_src = false;
     w->h.src_dirty = true;
     w->h.have_result = false;
     return w->h.src.upload((const float *) d, n, true);
 }
 int wavecu_icp_set_target(wavecu_icp *w, const float *xyzw, size_t n) {
     if (!w || (!xyzw && n)) return WAVECU_ERR_ARG;
+    w->h.tgt_is_user = true;
+    w->h.have_orig_tgt = false;
     w->h.have_result = false;
     return w->h.tgt.set_points(xyzw, n, false);
 }
 int wavecu_icp_set_target_device(wavecu_icp *w, const void *d, size_t n) {
     if (!w || (!d && n)) return WAVECU_ERR_ARG;
+    w->h.tgt_is_user = true;
+    w->h.have_orig_tgt = false;
     w->h.have_result = false;
     return w->h.tgt.set_points((const float *) d, n, true);
 }
@@ -466,12 +814,7 @@ int wavecu_icp_align(wavecu_icp *w, double T_out[16], int *converged, int *itera
 
 int wavecu_icp_match(wavecu_icp *w, double T_out[16], int *converged, int *iterations) {
     if (!w) return WAVECU_ERR_ARG;
-    if (w->h.prm.res > 0) {
-        set_last_error("voxel-filtered / multiscale match() is not built yet: set res <= 0");
-        return WAVECU_ERR_STATE;
-    }
-    // full-resolution branch, src/icp.cpp:123-131
-    return w->h.align(T_out, converged, iterations, nullptr);
+    return w->h.match(T_out, converged, iterations);
 }
 
 int wavecu_icp_correspondences(wavecu_icp *w, int *idx_query, int *idx_match, float *dist2, size_t *n) {
@@ -539,11 +882,8 @@ int wavecu_icp_trace(wavecu_icp *w, double *mse, int *n_corr, float *T_inc, int 
 }
 
 int wavecu_icp_info(wavecu_icp *w, int method, double info_out[36]) {
-    (void) method;
-    (void) info_out;
-    if (!w) return WAVECU_ERR_ARG;
-    set_last_error("information estimators are not built yet");
-    return WAVECU_ERR_STATE;
+    if (!w || !info_out) return WAVECU_ERR_ARG;
+    return w->h.info(method, info_out);
 }
 
 int wavecu_icp_set_profiling(wavecu_icp *w, int enabled) {

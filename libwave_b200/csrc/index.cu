@@ -5,6 +5,7 @@
 
 #include "../../include/wavecu.h"
 #include "index.cuh"
+#include "voxel.cuh"
 
 namespace wavecu {
 
@@ -181,6 +182,14 @@ int grow(T *&ptr, size_t &cap, size_t want) {
 }
 
 }  // namespace
+
+void launch_bbox(const float4 *d_pts, size_t n, unsigned *d_bbox8, cudaStream_t stream) {
+    bbox_init_kernel<<<1, 32, 0, stream>>>(d_bbox8);
+    if (n) {
+        const int grid = (int) std::min<size_t>((n + kBuildThreads - 1) / kBuildThreads, 148 * 4);
+        bbox_kernel<<<grid, kBuildThreads, 0, stream>>>(d_pts, n, d_bbox8);
+    }
+}
 
 int MortonCloud::reserve(size_t n_points, size_t sorted_points) {
     if (n_points > cap) {

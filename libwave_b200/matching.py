@@ -164,10 +164,21 @@ class ICPMatcher(Matcher):
         self.converged, self.iterations = bool(conv.value), iters.value
         return T.reshape(4, 4).copy(), bool(conv.value), iters.value, capi.CONV_STATES[state.value]
 
-    def estimateInfo(self):
+    def info(self, method: int):
+        """One estimator on its own: INFO_LUM (estimateLUM) or INFO_LUMOLD (estimateLUMold)."""
         info = np.empty(36, dtype=np.float64)
-        capi.check(self._L.wavecu_icp_info(self._h, self.params.covar_estimator, _d(info)))
-        self.information = info.reshape(6, 6).copy()
+        capi.check(self._L.wavecu_icp_info(self._h, method, _d(info)))
+        return info.reshape(6, 6).copy()
+
+    def estimateInfo(self):
+        """ICPMatcher::estimateInfo (src/icp.cpp:135-142).  The reference's switch has no breaks:
+        LUM falls through to Censi and then LUMold, Censi falls through to LUMold - so whatever
+        covar_estimator says, `information` ends up as estimateLUMold's result.  That observable
+        behaviour is what is reproduced (the intermediate Censi matrix is never visible)."""
+        if self.params.covar_estimator == INFO_LUM:
+            self.information = self.info(INFO_LUM)
+        if self.params.covar_estimator in (INFO_LUM, INFO_CENSI, INFO_LUMOLD):
+            self.information = self.info(INFO_LUMOLD)
 
     # -- introspection ---------------------------------------------------------------------------
     def correspondences(self):
@@ -206,6 +217,15 @@ class ICPMatcher(Matcher):
         s = capi.StatsC()
         capi.check(self._L.wavecu_icp_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in capi.StatsC._fields_}
+
+
+def voxel_grid(cloud, leaf: float, device: int = 0):
+    """pcl::VoxelGrid<pcl::PointXYZ>::filter on the GPU; returns (xyzw, filtered)."""
+    a = _xyzw(cloud)
+    out = np.empty_like(a)
+    n, flag = C.c_size_t(), C.c_int()
+    capi.check(capi.lib().wavecu_voxel_grid(device, _f(a), a.shape[0], leaf, _f(out), C.byref(n), C.byref(flag)))
+    return out[:n.value].copy(), bool(flag.value)
 
 
 class NearestNeighbour:

@@ -130,3 +130,74 @@ void wo_rotation_from_sigma(const double *S9, double *R9) { rotation_from_sigma(
 int wo_solve6(const double *A36, const double *b6, double *x6) { return solve_pp<6>(A36, b6, x6) ? 1 : 0; }
 
 }  // extern "C"
+
+// ---- matcher level ------------------------------------------------------------------------------
+#include "matcher.hpp"
+
+extern "C" {
+
+// returns the number of output points; out must have room for n points
+size_t wo_voxel_grid(const float *in, size_t n, float leaf, float *out, int *filtered) {
+    std::vector<float> o;
+    const bool ok = voxel_grid(in, n, leaf, o);
+    if (filtered) *filtered = ok ? 1 : 0;
+    std::memcpy(out, o.data(), o.size() * sizeof(float));
+    return o.size() / 4;
+}
+
+void wo_transform_affine3d(const float *in, size_t n, const double *T16, float *out) {
+    transform_cloud_affine3d(in, n, T16, out);
+}
+
+struct wo_matcher_params_c {
+    double max_corr;
+    int max_iter;
+    double t_eps;
+    double fit_eps;
+    int multiscale_steps;
+    float res;
+    int sum_mode;
+};
+
+void *wo_icp_match(const float *ref, size_t n_ref, const float *tgt, size_t n_tgt, const wo_matcher_params_c *p,
+                   int nn_threads, int *success) {
+    MatcherParams mp;
+    mp.max_corr = p->max_corr;
+    mp.max_iter = p->max_iter;
+    mp.t_eps = p->t_eps;
+    mp.fit_eps = p->fit_eps;
+    mp.multiscale_steps = p->multiscale_steps;
+    mp.res = p->res;
+    mp.sum_mode = p->sum_mode;
+    MatchResult *r = new MatchResult();
+    *success = icp_match(ref, n_ref, tgt, n_tgt, mp, *r, nn_threads) ? 1 : 0;
+    return r;
+}
+
+void wo_match_summary(void *h, double *T16, int *levels, int *total_iters, size_t *n_ds_ref, size_t *n_ds_tgt) {
+    const MatchResult &r = *static_cast<MatchResult *>(h);
+    std::memcpy(T16, r.T, sizeof r.T);
+    *levels = r.levels;
+    *total_iters = r.total_iterations;
+    *n_ds_ref = r.ds_ref.size() / 4;
+    *n_ds_tgt = r.ds_tgt.size() / 4;
+}
+void wo_match_clouds(void *h, float *ds_ref, float *ds_tgt) {
+    const MatchResult &r = *static_cast<MatchResult *>(h);
+    std::memcpy(ds_ref, r.ds_ref.data(), r.ds_ref.size() * sizeof(float));
+    std::memcpy(ds_tgt, r.ds_tgt.data(), r.ds_tgt.size() * sizeof(float));
+}
+// the IcpResult of the last align(): usable with the wo_icp_result_* getters (do not free it)
+void *wo_match_last(void *h) { return &static_cast<MatchResult *>(h)->last; }
+void wo_match_free(void *h) { delete static_cast<MatchResult *>(h); }
+
+int wo_estimate_lum(const float *aligned, const float *target, const int *q, const int *m, size_t n, int sum_mode,
+                    int k, int k_ss, double *info36) {
+    return estimate_lum(aligned, target, q, m, n, sum_mode, k, k_ss, info36) ? 1 : 0;
+}
+int wo_estimate_lum_old(const float *aligned, size_t n_src, const float *target, size_t n_tgt, double max_corr,
+                        int sum_mode, int k, int k_ss, double *info36, int nn_threads) {
+    return estimate_lum_old(aligned, n_src, target, n_tgt, max_corr, sum_mode, k, k_ss, info36, nn_threads) ? 1 : 0;
+}
+
+}  // extern "C"

@@ -191,7 +191,7 @@ inline LumPair lum_pair(const float *a /*aligned source*/, const float *b /*targ
     return p;
 }
 
-bool lum_from_pairs(const std::vector<LumPair> &pr, int sum_mode, bool old_variant, double *info) {
+bool lum_from_pairs(const std::vector<LumPair> &pr, int sum_mode, bool old_variant, int k, int k_ss, double *info) {
     const int numCorr = (int) pr.size();
     double MM[36], MZ[6];
     for (int i = 0; i < 36; ++i) MM[i] = 0;
@@ -220,8 +220,7 @@ bool lum_from_pairs(const std::vector<LumPair> &pr, int sum_mode, bool old_varia
             MZ[5] += av[2] * df[0] - av[0] * df[2];
         }
     } else {
-        // the repo's estimator spec: the same float terms, summed exactly (2^-40 fixed point)
-        const int k = kLumShift;
+        // the repo's estimator spec: the same float terms, summed exactly in 2^-k fixed point
         Fix128 a[3], aa[6], dz[6];
         for (int ci = 0; ci != numCorr; ++ci) {
             const float *av = pr[ci].aver, *df = pr[ci].diff;
@@ -289,10 +288,10 @@ bool lum_from_pairs(const std::vector<LumPair> &pr, int sum_mode, bool old_varia
             const double e1 = df[1] - (D[1] + av[0] * D[4] - av[2] * D[3]);
             const double e2 = df[2] - (D[2] + av[1] * D[3] - av[0] * D[5]);
             const float term = static_cast<float>(e0 * e0 + e1 * e1 + e2 * e2);
-            if (std::isfinite(term)) acc.add((double) term, kLumShift);
-            else acc.add(0.0, kLumShift), ss = std::numeric_limits<float>::quiet_NaN();
+            if (std::isfinite(term)) acc.add((double) term, k_ss);
+            else ss = std::numeric_limits<float>::quiet_NaN();
         }
-        if (!std::isnan(ss)) ss = static_cast<float>(acc.value(kLumShift));
+        if (!std::isnan(ss)) ss = static_cast<float>(acc.value(k_ss));
     }
     bool failed = false;
     if (ss < 0.0000000000001 || !std::isfinite(ss)) {
@@ -308,17 +307,17 @@ bool lum_from_pairs(const std::vector<LumPair> &pr, int sum_mode, bool old_varia
 }  // namespace
 
 bool estimate_lum(const float *aligned, const float *target, const int *corr_q, const int *corr_m, size_t n_corr,
-                  int sum_mode, double *info) {
+                  int sum_mode, int k, int k_ss, double *info) {
     std::vector<LumPair> pr;
     pr.reserve(n_corr);
     for (size_t i = 0; i < n_corr; ++i) {
         if (corr_m[i] > -1) pr.push_back(lum_pair(aligned + 4 * (size_t) corr_q[i], target + 4 * (size_t) corr_m[i]));
     }
-    return lum_from_pairs(pr, sum_mode, false, info);
+    return lum_from_pairs(pr, sum_mode, false, k, k_ss, info);
 }
 
 bool estimate_lum_old(const float *aligned, size_t n_src, const float *target, size_t n_tgt, double max_corr,
-                      int sum_mode, double *info, int nn_threads) {
+                      int sum_mode, int k, int k_ss, double *info, int nn_threads) {
     KdTree tree(target, n_tgt, 4);
     Correspondences c;
     determine_correspondences(tree, aligned, n_src, max_corr, true /* d2 < max^2 */, c, nn_threads);
@@ -326,7 +325,7 @@ bool estimate_lum_old(const float *aligned, size_t n_src, const float *target, s
     pr.reserve(c.q.size());
     for (size_t i = 0; i < c.q.size(); ++i)
         pr.push_back(lum_pair(aligned + 4 * (size_t) c.q[i], target + 4 * (size_t) c.m[i]));
-    return lum_from_pairs(pr, sum_mode, true, info);
+    return lum_from_pairs(pr, sum_mode, true, k, k_ss, info);
 }
 
 }  // namespace wo

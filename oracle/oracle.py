@@ -185,3 +185,119 @@ def solve6(A, b):
     x = np.empty(6, dtype=np.float64)
     ok = lib().wo_solve6(_d(A), _d(b), _d(x))
     return x if ok else None
+
+
+# ---- matcher level (oracle/matcher.cpp) -----------------------------------------------------------
+class MatcherParamsC(C.Structure):
+    _fields_ = [("max_corr", C.c_double), ("max_iter", C.c_int), ("t_eps", C.c_double), ("fit_eps", C.c_double),
+                ("multiscale_steps", C.c_int), ("res", C.c_float), ("sum_mode", C.c_int)]
+
+
+def _declare_matcher(L):
+    L.wo_voxel_grid.restype = C.c_size_t
+    L.wo_voxel_grid.argtypes = [_fp, C.c_size_t, C.c_float, _fp, _ip]
+    L.wo_transform_affine3d.argtypes = [_fp, C.c_size_t, _dp, _fp]
+    L.wo_icp_match.restype = C.c_void_p
+    L.wo_icp_match.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, C.POINTER(MatcherParamsC), C.c_int, _ip]
+    L.wo_match_summary.argtypes = [C.c_void_p, _dp, _ip, _ip, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.wo_match_clouds.argtypes = [C.c_void_p, _fp, _fp]
+    L.wo_match_last.restype = C.c_void_p
+    L.wo_match_last.argtypes = [C.c_void_p]
+    L.wo_match_free.argtypes = [C.c_void_p]
+    L.wo_estimate_lum.restype = C.c_int
+    L.wo_estimate_lum.argtypes = [_fp, _fp, _ip, _ip, C.c_size_t, C.c_int, C.c_int, C.c_int, _dp]
+    L.wo_estimate_lum_old.restype = C.c_int
+    L.wo_estimate_lum_old.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_int, _dp,
+                                      C.c_int]
+
+
+_orig_declare = _declare
+
+
+def _declare(L):  # noqa: F811
+    _orig_declare(L)
+    _declare_matcher(L)
+
+
+def voxel_grid(cloud, leaf: float):
+    """pcl::VoxelGrid<PointXYZ>::filter; returns (xyzw, filtered_flag)."""
+    a = xyzw(cloud)
+    out = np.empty_like(a)
+    flag = C.c_int()
+    n = lib().wo_voxel_grid(_f(a), a.shape[0], leaf, _f(out), C.byref(flag))
+    return out[:n].copy(), bool(flag.value)
+
+
+def transform_affine3d(cloud, T):
+    a = xyzw(cloud)
+    T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+    out = np.empty_like(a)
+    lib().wo_transform_affine3d(_f(a), a.shape[0], _d(T), _f(out))
+    return out
+
+
+def _read_icp_result(h) -> IcpResult:
+    L = lib()
+    T = np.empty(16, dtype=np.float32)
+    conv, iters, state = C.c_int(), C.c_int(), C.c_int()
+    nc, nt, na = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    L.wo_icp_result_summary(h, _f(T), C.byref(conv), C.byref(iters), C.byref(state), C.byref(nc), C.byref(nt),
+                            C.byref(na))
+    r = IcpResult()
+    r.T = T.reshape(4, 4)
+    r.converged, r.iterations, r.state = bool(conv.value), iters.value, CONV_STATES[state.value]
+    r.corr_query = np.empty(nc.value, dtype=np.int32)
+    r.corr_match = np.empty(nc.value, dtype=np.int32)
+    r.corr_dist = np.empty(nc.value, dtype=np.float32)
+    L.wo_icp_result_corr(h, _i(r.corr_query), _i(r.corr_match), _f(r.corr_dist))
+    r.aligned = np.empty((na.value, 4), dtype=np.float32)
+    L.wo_icp_result_aligned(h, _f(r.aligned))
+    r.mse = np.empty(nt.value, dtype=np.float64)
+    r.n_corr = np.empty(nt.value, dtype=np.int32)
+    r.T_trace = np.empty((nt.value, 4, 4), dtype=np.float32)
+    L.wo_icp_result_trace(h, _d(r.mse), _i(r.n_corr), _f(r.T_trace))
+    return r
+
+
+class MatchResult:
+    pass
+
+
+def icp_match(ref, target, *, max_corr=3.0, max_iter=100, t_eps=1e-8, fit_eps=1e-2, multiscale_steps=3, res=0.1,
+              sum_mode=SUM_EXACT, nn_threads: int = 1) -> MatchResult:
+    """wave::ICPMatcher::match() restated (src/icp.cpp:75-133); defaults = icp.hpp:35-59."""
+    s, t = xyzw(ref), xyzw(target)
+    prm = MatcherParamsC(max_corr, max_iter, t_eps, fit_eps, multiscale_steps, res, sum_mode)
+    ok = C.c_int()
+    L = lib()
+    h = L.wo_icp_match(_f(s), s.shape[0], _f(t), t.shape[0], C.byref(prm), nn_threads, C.byref(ok))
+    T = np.empty(16, dtype=np.float64)
+    lv, it = C.c_int(), C.c_int()
+    nr, ntg = C.c_size_t(), C.c_size_t()
+    L.wo_match_summary(h, _d(T), C.byref(lv), C.byref(it), C.byref(nr), C.byref(ntg))
+    r = MatchResult()
+    r.success, r.T, r.levels, r.total_iterations = bool(ok.value), T.reshape(4, 4), lv.value, it.value
+    r.ds_ref = np.empty((nr.value, 4), dtype=np.float32)
+    r.ds_tgt = np.empty((ntg.value, 4), dtype=np.float32)
+    L.wo_match_clouds(h, _f(r.ds_ref), _f(r.ds_tgt))
+    r.last = _read_icp_result(L.wo_match_last(h))
+    L.wo_match_free(h)
+    return r
+
+
+def estimate_lum(aligned, target, corr_q, corr_m, sum_mode=SUM_EXACT, k_quad: int = 42):
+    """estimateLUM; k_quad = fix_scales(source, target, max_corr)[1] of the align() it follows."""
+    a, t = xyzw(aligned), xyzw(target)
+    q = np.ascontiguousarray(corr_q, dtype=np.int32)
+    m = np.ascontiguousarray(corr_m, dtype=np.int32)
+    info = np.empty(36, dtype=np.float64)
+    ok = lib().wo_estimate_lum(_f(a), _f(t), _i(q), _i(m), q.shape[0], sum_mode, k_quad - 2, k_quad - 4, _d(info))
+    return info.reshape(6, 6), bool(ok)
+
+
+def estimate_lum_old(aligned, target, max_corr, sum_mode=SUM_EXACT, k_quad: int = 42, nn_threads: int = 1):
+    a, t = xyzw(aligned), xyzw(target)
+    info = np.empty(36, dtype=np.float64)
+    ok = lib().wo_estimate_lum_old(_f(a), a.shape[0], _f(t), t.shape[0], max_corr, sum_mode, k_quad - 2, k_quad - 4,
+                                   _d(info), nn_threads)
+    return info.reshape(6, 6), bool(ok)

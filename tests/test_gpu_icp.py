@@ -97,3 +97,76 @@ def test_icp_fullres_bit_exact_vs_oracle(W, oracle, testscan, tx):
     pcl = oracle.icp_align(testscan, tgt, sum_mode=oracle.SUM_PCL, nn_threads=8)
     assert np.abs(m.getResult()[:3, 3] - pcl.T[:3, 3].astype(np.float64)).max() < 1e-4
     assert rot_angle(m.getResult()[:3, :3], pcl.T[:3, :3].astype(np.float64)) < 1e-5
+
+
+# ---- voxel grid, multiscale and information matrices (reference tests restated) --------------------
+@pytest.mark.parametrize("leaf", [0.05, 0.1, 0.8])
+def test_voxel_grid_bit_exact(W, oracle, testscan, leaf):
+    got, ok = W.voxel_grid(testscan, leaf)
+    ref, rok = oracle.voxel_grid(testscan, leaf)
+    assert ok == rok and got.shape == ref.shape
+    assert np.array_equal(got, ref)
+
+
+def test_voxel_grid_overflow_passthrough(W, oracle, testscan):
+    got, ok = W.voxel_grid(testscan[:5000], 1e-4)  # dx*dy*dz > INT_MAX: PCL returns the input
+    ref, rok = oracle.voxel_grid(testscan[:5000], 1e-4)
+    assert ok is False and rok is False
+    assert np.array_equal(got, ref)
+
+
+CASES = {
+    # name: (res, multiscale_steps, tx)   tests/icp_tests.cpp:65-148 with tests/config/icp.yaml
+    "nullDisplacement": (0.05, 0, 0.0),
+    "smallDisplacement": (0.05, 0, 0.2),
+    "multiscale": (0.1, 3, 0.2),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_reference_icp_cases_bit_exact(W, oracle, testscan, name):
+    res, steps, tx = CASES[name]
+    T = np.eye(4)
+    T[0, 3] = tx
+    tgt = pcl_transform(testscan, T)
+    m = W.ICPMatcher(W.ICPMatcherParams(res=res, multiscale_steps=steps))
+    m.setup(testscan, tgt)
+    assert m.match() is True
+    assert np.linalg.norm(m.getResult() - T) < 0.1  # tests/icp_tests.cpp:37
+    ref = oracle.icp_match(testscan, tgt, res=res, multiscale_steps=steps, nn_threads=8)
+    assert ref.success
+    assert m.iterations == ref.total_iterations
+    assert np.array_equal(m.getResult(), ref.T)
+    q, mm, d2 = m.correspondences()
+    assert np.array_equal(q, ref.last.corr_query)
+    assert np.array_equal(mm, ref.last.corr_match)
+    assert np.array_equal(d2, ref.last.corr_dist)
+    assert np.array_equal(m.aligned()[:, :3], ref.last.aligned[:, :3])
+
+
+def test_information_lum_vs_lumold(W, oracle, testscan):
+    """smallinfo + lumvslum (tests/icp_tests.cpp:105-195): one scan is distorted by U(-0.3, 0.3)."""
+    rng = np.random.default_rng(0)
+    T = np.eye(4)
+    T[0, 3] = 0.2
+    tgt = pcl_transform(testscan, T).astype(np.float64)
+    tgt = (tgt + rng.uniform(-0.3, 0.3, tgt.shape)).astype(np.float32)
+    m = W.ICPMatcher(W.ICPMatcherParams(res=0.05, multiscale_steps=0, covar_estimator=W.INFO_LUMOLD))
+    m.setup(testscan, tgt)
+    m.match()
+    lum, lumold = m.info(W.INFO_LUM), m.info(W.INFO_LUMOLD)
+    assert lumold[0, 0] > 0
+    ref = oracle.icp_match(testscan, tgt, res=0.05, multiscale_steps=0, nn_threads=8)
+    k_quad = oracle.fix_scales(ref.ds_ref, ref.ds_tgt, 3.0)[1]
+    r_lum, _ = oracle.estimate_lum(ref.last.aligned, ref.ds_tgt, ref.last.corr_query, ref.last.corr_match,
+                                   oracle.SUM_EXACT, k_quad)
+    r_old, _ = oracle.estimate_lum_old(ref.last.aligned, ref.ds_tgt, 3.0, oracle.SUM_EXACT, k_quad, nn_threads=8)
+    assert np.array_equal(lum, r_lum)
+    assert np.array_equal(lumold, r_old)
+    # against the reference's own (sequential fp32/fp64) arithmetic
+    p_old, _ = oracle.estimate_lum_old(ref.last.aligned, ref.ds_tgt, 3.0, oracle.SUM_PCL, nn_threads=8)
+    assert np.allclose(lumold, p_old, rtol=1e-4)
+    # estimateInfo(): the switch falls through, the result is always LUMold's (src/icp.cpp:135-142)
+    m.params.covar_estimator = W.INFO_LUM
+    m.estimateInfo()
+    assert np.array_equal(m.getInfo(), lumold)
