@@ -6,14 +6,9 @@ the oracle's PCL-faithful fp32 arithmetic (BASELINE.json north_star tolerance)."
 import numpy as np
 import pytest
 
-from conftest import pcl_transform
+from conftest import pcl_transform, rot_angle
 
 pytestmark = pytest.mark.gpu
-
-
-def rot_angle(Ra, Rb):
-    c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
-    return float(np.arccos(np.clip(c, -1.0, 1.0)))
 
 
 @pytest.fixture(scope="module")
