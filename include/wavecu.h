@@ -1,8 +1,8 @@
 /* wavecu.h - the C ABI of the B200 registration hot path (libwavecu.so).
  *
  * This is the drop-in boundary for wave_matching's ICPMatcher / GICPMatcher / NDTMatcher::match():
- * plain pointers and sizes, no C++/torch types.  The C++ shim in include/wave/matching/*.hpp
- * (same class names and semantics as the reference headers) and the Python ctypes mirror in
+ * plain pointers and sizes, no C++/torch types.  The C++ shim under include/wave/matching/ (same
+ * class names and semantics as the reference headers) and the Python ctypes mirror in
  * libwave_b200/matching.py both sit on top of exactly these entry points.
  *
  * What each group replaces in the reference (paths relative to wave_matching/):

@@ -76,3 +76,20 @@ def test_product_never_imports_the_oracle():
             bad = re.search(r"(^|\n)\s*(from\s+oracle|import\s+oracle)|#include\s*[<\"][^>\"]*oracle|libwave_oracle|wo_[a-z]+_",
                             text)
             assert not bad, f"{path} reaches into the oracle: {bad.group(0)!r}"
+
+
+def test_cpp_shim_builds_and_links(built):
+    """The C++ drop-in (libwave_matching.so) and the native test binary build with g++ here."""
+    from libwave_b200 import build
+    so = build.build_shim()
+    assert so.exists() and (ROOT / "tests" / "cpp" / "_build" / "test_matching").exists()
+    lib = ctypes.CDLL(str(built), mode=ctypes.RTLD_GLOBAL)
+    assert lib is not None
+    shim = ctypes.CDLL(str(so))
+    # the mangled constructor / match of wave::ICPMatcher must be exported
+    import subprocess
+    syms = subprocess.run(["nm", "-DC", str(so)], capture_output=True, text=True).stdout
+    for name in ("wave::ICPMatcher::match()", "wave::ICPMatcher::setRef", "wave::ICPMatcher::estimateInfo()",
+                 "wave::ICPMatcherParams::ICPMatcherParams(", "wave::ConfigParser::load("):
+        assert name in syms, name
+    assert shim is not None
