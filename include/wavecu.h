@@ -21,6 +21,8 @@
  *                                  src/icp_pcl_functions.cpp:67-80
  *   wavecu_voxel_grid              pcl::VoxelGrid::filter, src/icp.cpp:81-90,106-113,
  *                                  src/gicp.cpp:39-40,49-50
+ *   wavecu_ndt_*                   pcl::NormalDistributionsTransform member + plumbing,
+ *                                  include/wave/matching/ndt.hpp:72, src/ndt.cpp:18-65
  *
  * Conventions: clouds are arrays of pcl::PointXYZ records = 4 floats (x, y, z, pad) = "xyzw";
  * 4x4 transforms are row-major doubles; every function returns 0 on success and a negative
@@ -139,6 +141,39 @@ int wavecu_nn_search(wavecu_nn *h, const float *q_xyzw, size_t nq, double max_di
  * `repeats` back-to-back searches measured with CUDA events on the handle's stream. */
 int wavecu_nn_search_device(wavecu_nn *h, const void *d_q_xyzw, size_t nq, double max_dist, void *d_idx,
                             void *d_dist2, int repeats, float *elapsed_ms);
+
+/* ---- NDTMatcher (include/wave/matching/ndt.hpp:33-80, src/ndt.cpp:18-65) ---------------------------
+ * Field-for-field mirror of wave::NDTMatcherParams (ndt.hpp:37-41); res is clamped to >= 0.05 as the
+ * reference constructor does (src/ndt.cpp:23-26). */
+typedef struct {
+    int step_size;   /* ndt.hpp:37 (an int in the reference), default 3 */
+    int max_iter;    /* ndt.hpp:38, default 100 */
+    double t_eps;    /* ndt.hpp:39, default 1e-8 */
+    float res;       /* ndt.hpp:40, default 5 */
+} wavecu_ndt_params;
+
+void wavecu_ndt_default_params(wavecu_ndt_params *p);
+
+typedef struct wavecu_ndt wavecu_ndt;
+int wavecu_ndt_create(const wavecu_ndt_params *params, int device, void *stream, wavecu_ndt **out);
+int wavecu_ndt_destroy(wavecu_ndt *h);
+int wavecu_ndt_set_params(wavecu_ndt *h, const wavecu_ndt_params *params);
+/* ndt.setInputSource / setInputTarget (src/ndt.cpp:48-56); the target call marks the voxel grid stale */
+int wavecu_ndt_set_source(wavecu_ndt *h, const float *xyzw, size_t n);
+int wavecu_ndt_set_target(wavecu_ndt *h, const float *xyzw, size_t n);
+int wavecu_ndt_set_source_device(wavecu_ndt *h, const void *d_xyzw, size_t n);
+int wavecu_ndt_set_target_device(wavecu_ndt *h, const void *d_xyzw, size_t n);
+/* ndt.align + hasConverged + getFinalTransformation (src/ndt.cpp:58-65) */
+int wavecu_ndt_match(wavecu_ndt *h, double T_out[16], int *converged, int *iterations);
+/* The normal-distribution cells of the target (>= 6 points, ascending voxel index): for parity tests
+ * and callers that want the map.  Arrays may be NULL; at most `capacity` cells are written. */
+int wavecu_ndt_grid(wavecu_ndt *h, int *n_cells, int *voxel, int *count, float *centroid3, double *mean3,
+                    double *icov9, int capacity);
+/* One computeDerivatives pass at pose6 = (x, y, z, roll, pitch, yaw) with the source transformed by the
+ * fp32 matrix T16: score, gradient (6) and Hessian (6x6, row major). */
+int wavecu_ndt_derivatives(wavecu_ndt *h, const double pose6[6], const float T16[16], double *score, double g6[6],
+                           double H36[36]);
+int wavecu_ndt_stats(wavecu_ndt *h, long long *kernel_launches, long long *derivative_passes, int *n_cells);
 
 /* pcl::VoxelGrid<pcl::PointXYZ>::filter (src/icp.cpp:81-90,106-113; src/gicp.cpp:39-40,49-50):
  * one centroid per occupied voxel in ascending voxel index; out_xyzw needs room for n points.

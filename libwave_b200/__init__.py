@@ -5,4 +5,4 @@ host-side mirror of the reference's matcher interface (matching.py).  ``synth`` 
 scan generator used by the tests and the bench.  Nothing here imports ``oracle/``.
 """
 from .matching import (EST_POINT_TO_PLANE, EST_SVD, INFO_CENSI, INFO_LUM, INFO_LUMOLD, ICPMatcher,  # noqa: F401
-                       ICPMatcherParams, Matcher, NearestNeighbour, voxel_grid)
+                       ICPMatcherParams, Matcher, NDTMatcher, NDTMatcherParams, NearestNeighbour, voxel_grid)

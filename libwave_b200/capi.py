@@ -26,6 +26,11 @@ class IcpParamsC(C.Structure):
                 ("res", C.c_float), ("covar_estimator", C.c_int), ("estimator", C.c_int)]
 
 
+class NdtParamsC(C.Structure):
+    """wavecu_ndt_params == wave::NDTMatcherParams (ndt.hpp:37-41)."""
+    _fields_ = [("step_size", C.c_int), ("max_iter", C.c_int), ("t_eps", C.c_double), ("res", C.c_float)]
+
+
 class StatsC(C.Structure):
     _fields_ = [("build_ms", C.c_double), ("iterate_ms", C.c_double), ("solve_ms", C.c_double),
                 ("total_ms", C.c_double), ("iterate_launches", C.c_longlong), ("kernel_launches", C.c_longlong),
@@ -61,6 +66,18 @@ SIGNATURES = {
     "wavecu_nn_set_target": (C.c_int, [_vp, _fp, _sz]),
     "wavecu_nn_search": (C.c_int, [_vp, _fp, _sz, C.c_double, _ip, _fp]),
     "wavecu_nn_search_device": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, C.c_int, _fp]),
+    "wavecu_ndt_default_params": (None, [C.POINTER(NdtParamsC)]),
+    "wavecu_ndt_create": (C.c_int, [C.POINTER(NdtParamsC), C.c_int, _vp, C.POINTER(_vp)]),
+    "wavecu_ndt_destroy": (C.c_int, [_vp]),
+    "wavecu_ndt_set_params": (C.c_int, [_vp, C.POINTER(NdtParamsC)]),
+    "wavecu_ndt_set_source": (C.c_int, [_vp, _fp, _sz]),
+    "wavecu_ndt_set_target": (C.c_int, [_vp, _fp, _sz]),
+    "wavecu_ndt_set_source_device": (C.c_int, [_vp, _vp, _sz]),
+    "wavecu_ndt_set_target_device": (C.c_int, [_vp, _vp, _sz]),
+    "wavecu_ndt_match": (C.c_int, [_vp, _dp, _ip, _ip]),
+    "wavecu_ndt_grid": (C.c_int, [_vp, _ip, _ip, _ip, _fp, _dp, _dp, C.c_int]),
+    "wavecu_ndt_derivatives": (C.c_int, [_vp, _dp, _fp, _dp, _dp, _dp]),
+    "wavecu_ndt_stats": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _ip]),
     "wavecu_voxel_grid": (C.c_int, [C.c_int, _fp, _sz, C.c_float, _fp, _szp, _ip]),
     "wavecu_last_error": (C.c_char_p, []),
     "wavecu_device_count": (C.c_int, []),

@@ -1,0 +1,890 @@
+// NDTMatcher on the device (wavecu_ndt_*): replaces pcl::NormalDistributionsTransform as the
+// reference drives it (wave_matching/src/ndt.cpp:18-65; PCL 1.8 registration/impl/ndt.hpp and
+// filters/impl/voxel_grid_covariance.hpp).
+//
+//   grid build   VoxelGridCovariance: voxel keys + stable sort (shared with VoxelGrid), then one
+//                thread per occupied voxel accumulates, in cloud order, the fp32 centroid (what PCL's
+//                radius search runs on) and the fp64 sum / sum of outer products, forms the
+//                covariance, clamps its small eigenvalues to 0.01 * largest (3x3 Jacobi in fp64)
+//                and inverts it; voxels with >= 6 points go into an open-addressing hash table
+//                keyed by voxel index.
+//   derivatives  computeDerivatives: one thread per source point transforms it (fp32 4x4), probes
+//                the 27 voxels around it - a centroid within `res` of the point can only live there,
+//                which replaces PCL's kd-tree radius search over the centroids - and accumulates
+//                score, gradient (6) and Hessian (21 unique) in fp64; per-block partial sums are
+//                combined in a fixed order by a second kernel (deterministic).
+//   host         Newton step through a 6x6 SVD solve and PCL's computeStepLengthMT, including its
+//                PCL 1.8 behaviour that the More-Thuente loop is skipped whenever step_max > step_min.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/wavecu.h"
+#include "index.cuh"
+#include "voxel.cuh"
+
+namespace wavecu {
+
+namespace {
+
+struct NdtLeafDev {
+    double mean[3];
+    double icov[6];  // xx xy xz yy yz zz
+    float centroid[3];
+    int voxel;
+    int n;
+    int valid;
+};
+
+constexpr int kNdtThreads = 128;
+constexpr int kNdtVals = 28;  // score, gradient 6, Hessian upper triangle 21
+
+// symmetric 3x3 eigen-decomposition (cyclic Jacobi, fp64); eigenvalues ascending
+__device__ void eig_sym3(const double A_in[9], double evals[3], double V[9]) {
+    double A[3][3], Q[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            A[i][j] = A_in[3 * i + j];
+            Q[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 32; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off == 0.0) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (A[p][q] == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double qkp = Q[k][p], qkq = Q[k][q];
+                    Q[k][p] = c * qkp - s * qkq;
+                    Q[k][q] = s * qkp + c * qkq;
+                }
+            }
+    }
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (A[o1][o1] < A[o0][o0]) { const int t = o0; o0 = o1; o1 = t; }
+    if (A[o2][o2] < A[o1][o1]) { const int t = o1; o1 = o2; o2 = t; }
+    if (A[o1][o1] < A[o0][o0]) { const int t = o0; o0 = o1; o1 = t; }
+    const int order[3] = {o0, o1, o2};
+    for (int j = 0; j < 3; ++j) {
+        evals[j] = A[order[j]][order[j]];
+        for (int i = 0; i < 3; ++i) V[3 * i + j] = Q[i][order[j]];
+    }
+}
+
+// one thread per occupied voxel (head element of its run in the sorted arrays)
+__global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict__ in, const unsigned *__restrict__ keys,
+                                                       const unsigned *__restrict__ vals,
+                                                       const int *__restrict__ pos, size_t n, NdtLeafDev *leaves) {
+    const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = keys[i];
+    const bool head = (k != 0xffffffffu) && (i == 0 || keys[i - 1] != k);
+    if (!head) return;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    double s[3] = {0, 0, 0}, ss[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    size_t j = i;
+    for (; j < n && keys[j] == k; ++j) {
+        const float4 p = in[vals[j]];
+        cx = __fadd_rn(cx, p.x);
+        cy = __fadd_rn(cy, p.y);
+        cz = __fadd_rn(cz, p.z);
+        const double q[3] = {p.x, p.y, p.z};
+        for (int r = 0; r < 3; ++r) {
+            s[r] += q[r];
+            for (int c = 0; c < 3; ++c) ss[3 * r + c] += q[r] * q[c];
+        }
+    }
+    const int cnt = (int) (j - i);
+    NdtLeafDev leaf;
+    leaf.voxel = (int) k;
+    leaf.n = cnt;
+    leaf.valid = 0;
+    const float fn = (float) cnt;
+    leaf.centroid[0] = __fdiv_rn(cx, fn);
+    leaf.centroid[1] = __fdiv_rn(cy, fn);
+    leaf.centroid[2] = __fdiv_rn(cz, fn);
+    for (int d = 0; d < 3; ++d) leaf.mean[d] = s[d] / cnt;
+    for (int d = 0; d < 6; ++d) leaf.icov[d] = 0;
+    if (cnt >= 6) {  // min_points_per_voxel_
+        double cov[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                cov[3 * r + c] = (ss[3 * r + c] - 2 * (s[r] * leaf.mean[c])) / cnt + leaf.mean[r] * leaf.mean[c];
+        for (int q = 0; q < 9; ++q) cov[q] *= (cnt - 1.0) / cnt;
+        double ev[3], V[9];
+        eig_sym3(cov, ev, V);
+        if (!(ev[0] < 0 || ev[1] < 0 || ev[2] <= 0)) {
+            const double min_ev = 0.01 * ev[2];  // min_covar_eigvalue_mult_
+            if (ev[0] < min_ev) {
+                ev[0] = min_ev;
+                if (ev[1] < min_ev) ev[1] = min_ev;
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) {
+                        double acc = 0;
+                        for (int q = 0; q < 3; ++q) acc += V[3 * r + q] * ev[q] * V[3 * c + q];
+                        cov[3 * r + c] = acc;
+                    }
+            }
+            const double a = cov[0], b = cov[1], c = cov[2], d = cov[4], e = cov[5], f = cov[8];
+            const double det = a * (d * f - e * e) - b * (b * f - e * c) + c * (b * e - d * c);
+            if (det != 0.0 && isfinite(det)) {
+                const double id = 1.0 / det;
+                leaf.icov[0] = (d * f - e * e) * id;
+                leaf.icov[1] = (c * e - b * f) * id;
+                leaf.icov[2] = (b * e - c * d) * id;
+                leaf.icov[3] = (a * f - c * c) * id;
+                leaf.icov[4] = (b * c - a * e) * id;
+                leaf.icov[5] = (a * d - b * b) * id;
+                bool ok = true;
+                for (int q = 0; q < 6; ++q) ok = ok && isfinite(leaf.icov[q]);
+                leaf.valid = ok ? 1 : 0;
+            }
+        }
+    }
+    leaves[pos[i]] = leaf;
+}
+
+__device__ __forceinline__ unsigned hash_voxel(int v, unsigned mask) {
+    unsigned h = (unsigned) v * 2654435761u;
+    h ^= h >> 15;
+    return h & mask;
+}
+
+__global__ void ndt_hash_insert_kernel(const NdtLeafDev *__restrict__ leaves, int n_leaves, int *table_key,
+                                       int *table_slot, unsigned mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_leaves || !leaves[i].valid) return;
+    const int v = leaves[i].voxel;
+    unsigned h = hash_voxel(v, mask);
+    for (;;) {
+        const int prev = atomicCAS(&table_key[h], -1, v);
+        if (prev == -1 || prev == v) {
+            table_slot[h] = i;
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+struct NdtConsts {
+    float T[12];       // fp32 pose matrix applied to the source (transformPointCloud with a Matrix4f)
+    double ja[3], jb[3], jc[3], jd[3], je[3], jf[3], jg[3], jh[3];
+    double a2[3], a3[3], b2[3], b3[3], c2[3], c3[3], d1[3], d2[3], d3[3], e1[3], e2[3], e3[3], f1[3], f2[3], f3[3];
+    double gauss_d1, gauss_d2;
+    float r2;          // (float)(res * res): FLANN keeps centroids with d2 < r2
+    int with_hessian;
+    GridDesc grid;
+};
+
+__device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+__global__ void __launch_bounds__(kNdtThreads) ndt_derivative_kernel(const float4 *__restrict__ src, int n_src,
+                                                                     const NdtLeafDev *__restrict__ leaves,
+                                                                     const int *__restrict__ table_key,
+                                                                     const int *__restrict__ table_slot, unsigned mask,
+                                                                     const NdtConsts *__restrict__ kc, double *partial) {
+    __shared__ NdtConsts c;
+    for (int w = threadIdx.x; w < (int) (sizeof(NdtConsts) / 4); w += blockDim.x)
+        reinterpret_cast<int *>(&c)[w] = reinterpret_cast<const int *>(kc)[w];
+    __syncthreads();
+    double acc[kNdtVals];
+#pragma unroll
+    for (int i = 0; i < kNdtVals; ++i) acc[i] = 0.0;
+
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_src; idx += gridDim.x * blockDim.x) {
+        const float4 p = src[idx];
+        if (!finite3(p.x, p.y, p.z)) continue;
+        // ((m0*x + m1*y) + m2*z) + m3, fp32, separately rounded
+        const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c.T[0], p.x), __fmul_rn(c.T[1], p.y)), __fmul_rn(c.T[2], p.z)), c.T[3]);
+        const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c.T[4], p.x), __fmul_rn(c.T[5], p.y)), __fmul_rn(c.T[6], p.z)), c.T[7]);
+        const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c.T[8], p.x), __fmul_rn(c.T[9], p.y)), __fmul_rn(c.T[10], p.z)), c.T[11]);
+        const int i0 = (int) __fsub_rn(floorf(__fmul_rn(tx, c.grid.inv)), (float) c.grid.min_b[0]);
+        const int i1 = (int) __fsub_rn(floorf(__fmul_rn(ty, c.grid.inv)), (float) c.grid.min_b[1]);
+        const int i2 = (int) __fsub_rn(floorf(__fmul_rn(tz, c.grid.inv)), (float) c.grid.min_b[2]);
+        const double x[3] = {p.x, p.y, p.z};
+        bool have_point_terms = false;
+        double J[3][6], Hp[9][3];  // Hp: a b c d e f (eq. 6.21) -> rows 0..5, padded
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int v0 = i0 + dx, v1 = i1 + dy, v2 = i2 + dz;
+                    if (v0 < 0 || v1 < 0 || v2 < 0 || v0 >= c.grid.div_b[0] || v1 >= c.grid.div_b[1] || v2 >= c.grid.div_b[2])
+                        continue;
+                    const int vox = v0 * c.grid.mul[0] + v1 * c.grid.mul[1] + v2 * c.grid.mul[2];
+                    unsigned h = hash_voxel(vox, mask);
+                    int slot = -1;
+                    for (;;) {
+                        const int key = __ldg(table_key + h);
+                        if (key == vox) {
+                            slot = __ldg(table_slot + h);
+                            break;
+                        }
+                        if (key == -1) break;
+                        h = (h + 1) & mask;
+                    }
+                    if (slot < 0) continue;
+                    const NdtLeafDev &cell = leaves[slot];
+                    const float dc = l2_simple(tx, ty, tz, cell.centroid[0], cell.centroid[1], cell.centroid[2]);
+                    if (!(dc < c.r2)) continue;
+                    if (!have_point_terms) {  // computePointDerivatives, once per point
+                        have_point_terms = true;
+                        for (int r = 0; r < 3; ++r)
+                            for (int q = 0; q < 6; ++q) J[r][q] = (r == q) ? 1.0 : 0.0;
+                        J[1][3] = dot3(x, c.ja);
+                        J[2][3] = dot3(x, c.jb);
+                        J[0][4] = dot3(x, c.jc);
+                        J[1][4] = dot3(x, c.jd);
+                        J[2][4] = dot3(x, c.je);
+                        J[0][5] = dot3(x, c.jf);
+                        J[1][5] = dot3(x, c.jg);
+                        J[2][5] = dot3(x, c.jh);
+                        if (c.with_hessian) {
+                            Hp[0][0] = 0; Hp[0][1] = dot3(x, c.a2); Hp[0][2] = dot3(x, c.a3);
+                            Hp[1][0] = 0; Hp[1][1] = dot3(x, c.b2); Hp[1][2] = dot3(x, c.b3);
+                            Hp[2][0] = 0; Hp[2][1] = dot3(x, c.c2); Hp[2][2] = dot3(x, c.c3);
+                            Hp[3][0] = dot3(x, c.d1); Hp[3][1] = dot3(x, c.d2); Hp[3][2] = dot3(x, c.d3);
+                            Hp[4][0] = dot3(x, c.e1); Hp[4][1] = dot3(x, c.e2); Hp[4][2] = dot3(x, c.e3);
+                            Hp[5][0] = dot3(x, c.f1); Hp[5][1] = dot3(x, c.f2); Hp[5][2] = dot3(x, c.f3);
+                        }
+                    }
+                    const double xt[3] = {(double) tx - cell.mean[0], (double) ty - cell.mean[1], (double) tz - cell.mean[2]};
+                    const double C00 = cell.icov[0], C01 = cell.icov[1], C02 = cell.icov[2], C11 = cell.icov[3],
+                                 C12 = cell.icov[4], C22 = cell.icov[5];
+                    const double Cx[3] = {C00 * xt[0] + C01 * xt[1] + C02 * xt[2], C01 * xt[0] + C11 * xt[1] + C12 * xt[2],
+                                          C02 * xt[0] + C12 * xt[1] + C22 * xt[2]};
+                    double e = exp(-c.gauss_d2 * dot3(xt, Cx) / 2);
+                    const double score_inc = -c.gauss_d1 * e;
+                    e = c.gauss_d2 * e;
+                    if (e > 1 || e < 0 || e != e) continue;  // the score increment is dropped with it
+                    e *= c.gauss_d1;
+                    double cJ[6][3], xcJ[6];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        cJ[q][0] = C00 * J[0][q] + C01 * J[1][q] + C02 * J[2][q];
+                        cJ[q][1] = C01 * J[0][q] + C11 * J[1][q] + C12 * J[2][q];
+                        cJ[q][2] = C02 * J[0][q] + C12 * J[1][q] + C22 * J[2][q];
+                        xcJ[q] = dot3(xt, cJ[q]);
+                    }
+                    acc[0] += score_inc;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) acc[1 + q] += xcJ[q] * e;
+                    if (c.with_hessian) {
+                        int u = 7;
+#pragma unroll
+                        for (int a = 0; a < 6; ++a)
+#pragma unroll
+                            for (int b = a; b < 6; ++b) {
+                                double second = 0.0;  // x'^T C^-1 d2T/dpa dpb: only the rotational 3x3 block
+                                if (a >= 3) {
+                                    // (3,3)=a (3,4)=b (3,5)=c (4,4)=d (4,5)=e (5,5)=f
+                                    const int row = (a == 3) ? (b - 3) : (a == 4 ? b - 1 : 5);
+                                    second = Cx[0] * Hp[row][0] + Cx[1] * Hp[row][1] + Cx[2] * Hp[row][2];
+                                }
+                                const double JbCJa = J[0][b] * cJ[a][0] + J[1][b] * cJ[a][1] + J[2][b] * cJ[a][2];
+                                acc[u++] += e * (-c.gauss_d2 * xcJ[a] * xcJ[b] + second + JbCJa);
+                            }
+                    }
+                }
+    }
+    // block reduction: warp shuffles, then one partial row per block
+    __shared__ double s_red[kNdtThreads / 32][kNdtVals];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kNdtVals; ++i) {
+        double v = acc[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNdtVals) {
+        double v = 0;
+        for (int w = 0; w < kNdtThreads / 32; ++w) v += s_red[w][threadIdx.x];
+        partial[(size_t) blockIdx.x * kNdtVals + threadIdx.x] = v;
+    }
+}
+
+__global__ void ndt_final_sum_kernel(const double *__restrict__ partial, int n_blocks, double *out) {
+    const int i = threadIdx.x;
+    if (i >= kNdtVals) return;
+    double v = 0;
+    for (int b = 0; b < n_blocks; ++b) v += partial[(size_t) b * kNdtVals + i];
+    out[i] = v;
+}
+
+// ---- host-side numerics of the optimiser (fp64) ------------------------------------------------------
+void svd_solve6(const double H[36], const double b[6], double x[6]) {
+    // x = pinv(H) b by one-sided Jacobi; singular values <= eps * 6 * sigma_max are dropped
+    // (Eigen::JacobiSVD::solve with its default threshold)
+    double A[6][6], V[6][6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            A[i][j] = H[6 * i + j];
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < 5; ++p)
+            for (int q = p + 1; q < 6; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int k = 0; k < 6; ++k) {
+                    alpha += A[k][p] * A[k][p];
+                    beta += A[k][q] * A[k][q];
+                    gamma += A[k][p] * A[k][q];
+                }
+                if (gamma == 0.0 || std::fabs(gamma) <= 1e-300) continue;
+                if (std::fabs(gamma) <= 2.220446049250313e-16 * std::sqrt(alpha * beta)) continue;
+                rotated = true;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+                for (int k = 0; k < 6; ++k) {
+                    const double ap = A[k][p], aq = A[k][q];
+                    A[k][p] = c * ap - s * aq;
+                    A[k][q] = s * ap + c * aq;
+                    const double vp = V[k][p], vq = V[k][q];
+                    V[k][p] = c * vp - s * vq;
+                    V[k][q] = s * vp + c * vq;
+                }
+            }
+        if (!rotated) break;
+    }
+    double sig[6], smax = 0;
+    for (int j = 0; j < 6; ++j) {
+        double s = 0;
+        for (int k = 0; k < 6; ++k) s += A[k][j] * A[k][j];
+        sig[j] = std::sqrt(s);
+        smax = std::max(smax, sig[j]);
+    }
+    const double thr = 2.220446049250313e-16 * 6 * smax;
+    for (int i = 0; i < 6; ++i) x[i] = 0;
+    for (int j = 0; j < 6; ++j) {
+        if (!(sig[j] > thr)) continue;
+        double ub = 0;
+        for (int k = 0; k < 6; ++k) ub += A[k][j] * b[k];
+        const double coef = ub / (sig[j] * sig[j]);
+        for (int i = 0; i < 6; ++i) x[i] += V[i][j] * coef;
+    }
+}
+
+// (Translation * AngleAxis(rx, X) * AngleAxis(ry, Y) * AngleAxis(rz, Z)).matrix(), Scalar = float
+void pose_to_matrix4f(const double p[6], float T[16]) {
+    const float rx = static_cast<float>(p[3]), ry = static_cast<float>(p[4]), rz = static_cast<float>(p[5]);
+    const float cx = std::cos(rx), sx = std::sin(rx), cy = std::cos(ry), sy = std::sin(ry), cz = std::cos(rz),
+                sz = std::sin(rz);
+    for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    T[0] = cy * cz;
+    T[1] = -cy * sz;
+    T[2] = sy;
+    T[4] = sx * sy * cz + cx * sz;
+    T[5] = -sx * sy * sz + cx * cz;
+    T[6] = -sx * cy;
+    T[8] = -cx * sy * cz + sx * sz;
+    T[9] = cx * sy * sz + sx * cz;
+    T[10] = cx * cy;
+    T[3] = static_cast<float>(p[0]);
+    T[7] = static_cast<float>(p[1]);
+    T[11] = static_cast<float>(p[2]);
+}
+
+void set3(double *v, double a, double b, double c) {
+    v[0] = a;
+    v[1] = b;
+    v[2] = c;
+}
+
+// computeAngleDerivatives (eq. 6.19 / 6.21) with PCL's |angle| < 10e-5 shortcut
+void angle_terms(const double p[6], NdtConsts &t) {
+    double cx, cy, cz, sx, sy, sz;
+    if (std::fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = std::cos(p[3]); sx = std::sin(p[3]); }
+    if (std::fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = std::cos(p[4]); sy = std::sin(p[4]); }
+    if (std::fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = std::cos(p[5]); sz = std::sin(p[5]); }
+    set3(t.ja, (-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy));
+    set3(t.jb, (cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy));
+    set3(t.jc, (-sy * cz), sy * sz, cy);
+    set3(t.jd, sx * cy * cz, (-sx * cy * sz), sx * sy);
+    set3(t.je, (-cx * cy * cz), cx * cy * sz, (-cx * sy));
+    set3(t.jf, (-cy * sz), (-cy * cz), 0);
+    set3(t.jg, (cx * cz - sx * sy * sz), (-cx * sz - sx * sy * cz), 0);
+    set3(t.jh, (sx * cz + cx * sy * sz), (cx * sy * cz - sx * sz), 0);
+    set3(t.a2, (-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), sx * cy);
+    set3(t.a3, (-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), (-cx * cy));
+    set3(t.b2, (cx * cy * cz), (-cx * cy * sz), (cx * sy));
+    set3(t.b3, (sx * cy * cz), (-sx * cy * sz), (sx * sy));
+    set3(t.c2, (-sx * cz - cx * sy * sz), (sx * sz - cx * sy * cz), 0);
+    set3(t.c3, (cx * cz - sx * sy * sz), (-sx * sy * cz - cx * sz), 0);
+    set3(t.d1, (-cy * cz), (cy * sz), (sy));
+    set3(t.d2, (-sx * sy * cz), (sx * sy * sz), (sx * cy));
+    set3(t.d3, (cx * sy * cz), (-cx * sy * sz), (-cx * cy));
+    set3(t.e1, (sy * sz), (sy * cz), 0);
+    set3(t.e2, (-sx * cy * sz), (-sx * cy * cz), 0);
+    set3(t.e3, (cx * cy * sz), (cx * cy * cz), 0);
+    set3(t.f1, (-cy * cz), (cy * sz), 0);
+    set3(t.f2, (-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), 0);
+    set3(t.f3, (-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), 0);
+}
+
+double psi_mt(double a, double f_a, double f_0, double g_0, double mu) { return f_a - f_0 - mu * g_0 * a; }
+double dpsi_mt(double g_a, double g_0, double mu) { return g_a - mu * g_0; }
+
+bool update_interval_mt(double &a_l, double &f_l, double &g_l, double &a_u, double &f_u, double &g_u, double a_t,
+                        double f_t, double g_t) {
+    if (f_t > f_l) {  // case U1 / a
+        a_u = a_t; f_u = f_t; g_u = g_t;
+        return false;
+    }
+    if (g_t * (a_l - a_t) > 0) {  // case U2 / b
+        a_l = a_t; f_l = f_t; g_l = g_t;
+        return false;
+    }
+    if (g_t * (a_l - a_t) < 0) {  // case U3 / c
+        a_u = a_l; f_u = f_l; g_u = g_l;
+        a_l = a_t; f_l = f_t; g_l = g_t;
+        return false;
+    }
+    return true;
+}
+
+double cubic_min(double a_1, double f_1, double g_1, double a_2, double f_2, double g_2) {
+    // minimiser of the cubic through (a_1, f_1, g_1), (a_2, f_2, g_2) [Sun & Yuan 2006, eq. 2.4.52 / 2.4.56]
+    const double z = 3 * (f_2 - f_1) / (a_2 - a_1) - g_2 - g_1;
+    const double w = std::sqrt(z * z - g_2 * g_1);
+    return a_1 + (a_2 - a_1) * (w - g_1 - z) / (g_2 - g_1 + 2 * w);
+}
+
+double trial_value_mt(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t,
+                      double g_t) {
+    if (f_t > f_l) {  // case 1
+        const double a_c = cubic_min(a_l, f_l, g_l, a_t, f_t, g_t);
+        const double a_q = a_l - 0.5 * (a_l - a_t) * g_l / (g_l - (f_l - f_t) / (a_l - a_t));
+        return (std::fabs(a_c - a_l) < std::fabs(a_q - a_l)) ? a_c : 0.5 * (a_q + a_c);
+    }
+    if (g_t * g_l < 0) {  // case 2
+        const double a_c = cubic_min(a_l, f_l, g_l, a_t, f_t, g_t);
+        const double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+        return (std::fabs(a_c - a_t) >= std::fabs(a_s - a_t)) ? a_c : a_s;
+    }
+    if (std::fabs(g_t) <= std::fabs(g_l)) {  // case 3
+        const double a_c = cubic_min(a_l, f_l, g_l, a_t, f_t, g_t);
+        const double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+        const double a_t_next = (std::fabs(a_c - a_t) < std::fabs(a_s - a_t)) ? a_c : a_s;
+        return (a_t > a_l) ? std::min(a_t + 0.66 * (a_u - a_t), a_t_next) : std::max(a_t + 0.66 * (a_u - a_t), a_t_next);
+    }
+    return cubic_min(a_u, f_u, g_u, a_t, f_t, g_t);  // case 4
+}
+
+}  // namespace
+
+struct NdtHandle {
+    wavecu_ndt_params prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    float4 *d_src = nullptr, *d_tgt = nullptr;
+    size_t n_src = 0, n_tgt = 0, src_cap = 0, tgt_cap = 0;
+    bool grid_dirty = true;
+    VoxelWork vox;
+    NdtLeafDev *d_leaves = nullptr;
+    size_t leaf_cap = 0;
+    int n_leaves = 0;
+    int *d_table_key = nullptr, *d_table_slot = nullptr;
+    size_t table_cap = 0;
+    unsigned table_mask = 0;
+    float resolution = 1.f;
+    GridDesc grid{};
+    bool grid_ok = false;
+    NdtConsts *d_consts = nullptr;
+    double *d_partial = nullptr, *d_sums = nullptr, *h_sums = nullptr;
+    int n_blocks = 0;
+    long long launches = 0;
+    long long derivative_passes = 0;
+    float final_T[16];
+
+    int init() {
+        WCU_CHECK(cudaSetDevice(device));
+        if (!stream) {
+            WCU_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            own_stream = true;
+        }
+        vox.device = device;
+        vox.stream = stream;
+        n_blocks = 148 * 4;
+        WCU_CHECK(cudaMalloc((void **) &d_consts, sizeof(NdtConsts)));
+        WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(double) * kNdtVals * (size_t) n_blocks));
+        WCU_CHECK(cudaMalloc((void **) &d_sums, sizeof(double) * kNdtVals));
+        WCU_CHECK(cudaHostAlloc((void **) &h_sums, sizeof(double) * kNdtVals, cudaHostAllocDefault));
+        return WAVECU_OK;
+    }
+
+    int upload(float4 *&dst, size_t &cap, size_t &n_dst, const float *xyzw, size_t n, bool from_device) {
+        WCU_CHECK(cudaSetDevice(device));
+        if (n > cap) {
+            if (dst) WCU_CHECK(cudaFree(dst));
+            dst = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &dst, (n + 64) * sizeof(float4)));
+            cap = n + 64;
+        }
+        n_dst = n;
+        if (n)
+            WCU_CHECK(cudaMemcpyAsync(dst, xyzw, n * sizeof(float4),
+                                      from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+        return WAVECU_OK;
+    }
+
+    float clamped_res() const { return prm.res < 0.05f ? 0.05f : prm.res; }  // src/ndt.cpp:23-26
+
+    int build_grid() {
+        resolution = clamped_res();
+        grid_ok = false;
+        n_leaves = 0;
+        grid_dirty = false;
+        if (n_tgt == 0) return WAVECU_OK;
+        int status = 0;
+        int rc = vox.prepare(d_tgt, n_tgt, resolution, &status);
+        if (rc) return rc;
+        if (status != 1) return WAVECU_OK;  // overflow: VoxelGridCovariance clears its output -> no cells
+        grid = vox.grid;
+        n_leaves = vox.n_voxels;
+        if ((size_t) n_leaves > leaf_cap) {
+            if (d_leaves) WCU_CHECK(cudaFree(d_leaves));
+            d_leaves = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &d_leaves, ((size_t) n_leaves + 64) * sizeof(NdtLeafDev)));
+            leaf_cap = (size_t) n_leaves + 64;
+        }
+        size_t slots = 64;
+        while (slots < 2 * (size_t) n_leaves) slots <<= 1;
+        if (slots > table_cap) {
+            if (d_table_key) WCU_CHECK(cudaFree(d_table_key));
+            if (d_table_slot) WCU_CHECK(cudaFree(d_table_slot));
+            d_table_key = d_table_slot = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &d_table_key, slots * sizeof(int)));
+            WCU_CHECK(cudaMalloc((void **) &d_table_slot, slots * sizeof(int)));
+            table_cap = slots;
+        }
+        table_mask = (unsigned) (slots - 1);
+        WCU_CHECK(cudaMemsetAsync(d_table_key, 0xff, slots * sizeof(int), stream));
+        ndt_leaf_kernel<<<(unsigned) ((n_tgt + 255) / 256), 256, 0, stream>>>(d_tgt, vox.d_keys, vox.d_vals, vox.d_pos,
+                                                                              n_tgt, d_leaves);
+        if (n_leaves)
+            ndt_hash_insert_kernel<<<(n_leaves + 255) / 256, 256, 0, stream>>>(d_leaves, n_leaves, d_table_key,
+                                                                               d_table_slot, table_mask);
+        launches += 2;
+        WCU_CHECK(cudaGetLastError());
+        grid_ok = true;
+        return WAVECU_OK;
+    }
+
+    // computeDerivatives at pose p (the source is transformed by the fp32 matrix of p)
+    int derivatives(const double p[6], const float T[16], double gd1, double gd2, bool with_hessian, double *score,
+                    double g[6], double H[36]) {
+        NdtConsts c;
+        std::memcpy(c.T, T, sizeof(float) * 12);
+        angle_terms(p, c);
+        c.gauss_d1 = gd1;
+        c.gauss_d2 = gd2;
+        c.r2 = static_cast<float>((double) resolution * (double) resolution);
+        c.with_hessian = with_hessian ? 1 : 0;
+        c.grid = grid;
+        WCU_CHECK(cudaMemcpyAsync(d_consts, &c, sizeof c, cudaMemcpyHostToDevice, stream));
+        ndt_derivative_kernel<<<n_blocks, kNdtThreads, 0, stream>>>(d_src, (int) n_src, d_leaves, d_table_key,
+                                                                     d_table_slot, table_mask, d_consts, d_partial);
+        ndt_final_sum_kernel<<<1, 32, 0, stream>>>(d_partial, n_blocks, d_sums);
+        launches += 2;
+        ++derivative_passes;
+        WCU_CHECK(cudaMemcpyAsync(h_sums, d_sums, sizeof(double) * kNdtVals, cudaMemcpyDeviceToHost, stream));
+        WCU_CHECK(cudaStreamSynchronize(stream));
+        WCU_CHECK(cudaGetLastError());
+        *score = h_sums[0];
+        for (int i = 0; i < 6; ++i) g[i] = h_sums[1 + i];
+        if (with_hessian) {
+            int u = 7;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b) {
+                    H[6 * a + b] = H[6 * b + a] = h_sums[u];
+                    ++u;
+                }
+        }
+        return WAVECU_OK;
+    }
+
+    int match(double *T_out, int *converged_out, int *iterations_out) {
+        WCU_CHECK(cudaSetDevice(device));
+        for (int i = 0; i < 16; ++i) final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+        launches = 0;
+        derivative_passes = 0;
+        bool converged = false;
+        int nr_iterations = 0;
+        if (grid_dirty || clamped_res() != resolution) {
+            const int rc = build_grid();
+            if (rc) return rc;
+        }
+        if (n_src && n_tgt && grid_ok) {
+            const double outlier_ratio = 0.55;
+            const double c1 = 10 * (1 - outlier_ratio);
+            const double c2 = outlier_ratio / std::pow((double) resolution, 3);
+            const double d3 = -std::log(c2);
+            const double gd1 = -std::log(c1 + c2) - d3;
+            const double gd2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / gd1);
+            const double step_max = (double) prm.step_size, step_min = prm.t_eps / 2;
+            double p[6] = {0, 0, 0, 0, 0, 0}, g[6], H[36], score = 0;
+            int rc = derivatives(p, final_T, gd1, gd2, true, &score, g, H);
+            if (rc) return rc;
+            while (!converged) {
+                double neg_g[6], dir[6];
+                for (int i = 0; i < 6; ++i) neg_g[i] = -g[i];
+                svd_solve6(H, neg_g, dir);
+                double nrm = 0;
+                for (int i = 0; i < 6; ++i) nrm += dir[i] * dir[i];
+                double delta_p_norm = std::sqrt(nrm);
+                if (delta_p_norm == 0 || delta_p_norm != delta_p_norm) {
+                    converged = delta_p_norm == delta_p_norm;
+                    break;
+                }
+                for (int i = 0; i < 6; ++i) dir[i] /= delta_p_norm;
+                // ---- computeStepLengthMT ----
+                double a_t = 0;
+                const double phi_0 = -score;
+                double d_phi_0 = 0;
+                for (int i = 0; i < 6; ++i) d_phi_0 -= g[i] * dir[i];
+                bool have_step = true;
+                if (d_phi_0 >= 0) {
+                    if (d_phi_0 == 0) have_step = false;  // return 0
+                    else {
+                        d_phi_0 *= -1;
+                        for (int i = 0; i < 6; ++i) dir[i] *= -1;
+                    }
+                }
+                if (have_step) {
+                    const double mu = 1.e-4, nu = 0.9;
+                    double a_l = 0, a_u = 0;
+                    double f_l = psi_mt(a_l, phi_0, phi_0, d_phi_0, mu), g_l = dpsi_mt(d_phi_0, d_phi_0, mu);
+                    double f_u = psi_mt(a_u, phi_0, phi_0, d_phi_0, mu), g_u = dpsi_mt(d_phi_0, d_phi_0, mu);
+                    // PCL 1.8: true whenever step_max > step_min, which skips the loop below
+                    bool interval_converged = (step_max - step_min) > 0, open_interval = true;
+                    a_t = std::max(std::min(delta_p_norm, step_max), step_min);
+                    double x_t[6];
+                    auto evaluate = [&](bool hess) -> int {
+                        for (int i = 0; i < 6; ++i) x_t[i] = p[i] + dir[i] * a_t;
+                        pose_to_matrix4f(x_t, final_T);
+                        return derivatives(x_t, final_T, gd1, gd2, hess, &score, g, H);
+                    };
+                    rc = evaluate(true);
+                    if (rc) return rc;
+                    double phi_t = -score, d_phi_t = 0;
+                    for (int i = 0; i < 6; ++i) d_phi_t -= g[i] * dir[i];
+                    double psi_t = psi_mt(a_t, phi_t, phi_0, d_phi_0, mu), d_psi_t = dpsi_mt(d_phi_t, d_phi_0, mu);
+                    int step_iterations = 0;
+                    while (!interval_converged && step_iterations < 10 && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
+                        a_t = open_interval ? trial_value_mt(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t)
+                                            : trial_value_mt(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+                        a_t = std::max(std::min(a_t, step_max), step_min);
+                        rc = evaluate(false);
+                        if (rc) return rc;
+                        phi_t = -score;
+                        d_phi_t = 0;
+                        for (int i = 0; i < 6; ++i) d_phi_t -= g[i] * dir[i];
+                        psi_t = psi_mt(a_t, phi_t, phi_0, d_phi_0, mu);
+                        d_psi_t = dpsi_mt(d_phi_t, d_phi_0, mu);
+                        if (open_interval && (psi_t <= 0 && d_psi_t >= 0)) {
+                            open_interval = false;
+                            f_l = f_l + phi_0 - mu * d_phi_0 * a_l;
+                            g_l = g_l + mu * d_phi_0;
+                            f_u = f_u + phi_0 - mu * d_phi_0 * a_u;
+                            g_u = g_u + mu * d_phi_0;
+                        }
+                        interval_converged = open_interval
+                                               ? update_interval_mt(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t)
+                                               : update_interval_mt(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+                        ++step_iterations;
+                    }
+                    if (step_iterations) {  // computeHessian at the accepted point
+                        double g_keep[6], s_keep = score;
+                        std::memcpy(g_keep, g, sizeof g);
+                        rc = derivatives(x_t, final_T, gd1, gd2, true, &score, g, H);
+                        if (rc) return rc;
+                        std::memcpy(g, g_keep, sizeof g);
+                        score = s_keep;
+                    }
+                }
+                delta_p_norm = a_t;
+                for (int i = 0; i < 6; ++i) p[i] = p[i] + dir[i] * delta_p_norm;
+                if (nr_iterations > prm.max_iter || (nr_iterations && (std::fabs(delta_p_norm) < prm.t_eps)))
+                    converged = true;
+                nr_iterations++;
+            }
+        }
+        if (T_out)
+            for (int i = 0; i < 16; ++i) T_out[i] = (double) final_T[i];
+        if (converged_out) *converged_out = converged ? 1 : 0;
+        if (iterations_out) *iterations_out = nr_iterations;
+        return WAVECU_OK;
+    }
+
+    void release() {
+        cudaSetDevice(device);
+        vox.release();
+        for (void *p : {(void *) d_src, (void *) d_tgt, (void *) d_leaves, (void *) d_table_key, (void *) d_table_slot,
+                        (void *) d_consts, (void *) d_partial, (void *) d_sums})
+            if (p) cudaFree(p);
+        if (h_sums) cudaFreeHost(h_sums);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace wavecu
+
+using namespace wavecu;
+
+struct wavecu_ndt {
+    NdtHandle h;
+};
+
+extern "C" {
+
+void wavecu_ndt_default_params(wavecu_ndt_params *p) {
+    if (!p) return;
+    p->step_size = 3;
+    p->max_iter = 100;
+    p->t_eps = 1e-8;
+    p->res = 5.f;
+}
+
+int wavecu_ndt_create(const wavecu_ndt_params *params, int device, void *stream, wavecu_ndt **out) {
+    if (!out) return WAVECU_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        set_last_error("no such CUDA device (libwavecu has no CPU fallback)");
+        return WAVECU_ERR_CUDA;
+    }
+    wavecu_ndt *w = new wavecu_ndt();
+    if (params) w->h.prm = *params;
+    else wavecu_ndt_default_params(&w->h.prm);
+    w->h.device = device;
+    w->h.stream = (cudaStream_t) stream;
+    const int rc = w->h.init();
+    if (rc) {
+        w->h.release();
+        delete w;
+        return rc;
+    }
+    *out = w;
+    return WAVECU_OK;
+}
+
+int wavecu_ndt_destroy(wavecu_ndt *w) {
+    if (!w) return WAVECU_OK;
+    w->h.release();
+    delete w;
+    return WAVECU_OK;
+}
+
+int wavecu_ndt_set_params(wavecu_ndt *w, const wavecu_ndt_params *params) {
+    if (!w || !params) return WAVECU_ERR_ARG;
+    w->h.prm = *params;
+    return WAVECU_OK;
+}
+
+int wavecu_ndt_set_source(wavecu_ndt *w, const float *xyzw, size_t n) {
+    if (!w || (!xyzw && n)) return WAVECU_ERR_ARG;
+    return w->h.upload(w->h.d_src, w->h.src_cap, w->h.n_src, xyzw, n, false);
+}
+int wavecu_ndt_set_source_device(wavecu_ndt *w, const void *d, size_t n) {
+    if (!w || (!d && n)) return WAVECU_ERR_ARG;
+    return w->h.upload(w->h.d_src, w->h.src_cap, w->h.n_src, (const float *) d, n, true);
+}
+int wavecu_ndt_set_target(wavecu_ndt *w, const float *xyzw, size_t n) {
+    if (!w || (!xyzw && n)) return WAVECU_ERR_ARG;
+    w->h.grid_dirty = true;
+    return w->h.upload(w->h.d_tgt, w->h.tgt_cap, w->h.n_tgt, xyzw, n, false);
+}
+int wavecu_ndt_set_target_device(wavecu_ndt *w, const void *d, size_t n) {
+    if (!w || (!d && n)) return WAVECU_ERR_ARG;
+    w->h.grid_dirty = true;
+    return w->h.upload(w->h.d_tgt, w->h.tgt_cap, w->h.n_tgt, (const float *) d, n, true);
+}
+
+int wavecu_ndt_match(wavecu_ndt *w, double T_out[16], int *converged, int *iterations) {
+    if (!w) return WAVECU_ERR_ARG;
+    return w->h.match(T_out, converged, iterations);
+}
+
+int wavecu_ndt_grid(wavecu_ndt *w, int *n_cells, int *voxel, int *count, float *centroid3, double *mean3, double *icov9,
+                    int capacity) {
+    if (!w || !n_cells) return WAVECU_ERR_ARG;
+    NdtHandle &h = w->h;
+    WCU_CHECK(cudaSetDevice(h.device));
+    if (h.grid_dirty || h.clamped_res() != h.resolution) {
+        const int rc = h.build_grid();
+        if (rc) return rc;
+    }
+    std::vector<NdtLeafDev> all((size_t) h.n_leaves);
+    if (h.n_leaves) {
+        WCU_CHECK(cudaMemcpyAsync(all.data(), h.d_leaves, sizeof(NdtLeafDev) * (size_t) h.n_leaves, cudaMemcpyDeviceToHost,
+                                  h.stream));
+        WCU_CHECK(cudaStreamSynchronize(h.stream));
+    }
+    int m = 0;
+    for (const NdtLeafDev &l : all) {
+        if (!l.valid) continue;
+        if (m < capacity) {
+            if (voxel) voxel[m] = l.voxel;
+            if (count) count[m] = l.n;
+            for (int d = 0; d < 3; ++d) {
+                if (centroid3) centroid3[3 * m + d] = l.centroid[d];
+                if (mean3) mean3[3 * m + d] = l.mean[d];
+            }
+            if (icov9) {
+                const double *c = l.icov;
+                const double full[9] = {c[0], c[1], c[2], c[1], c[3], c[4], c[2], c[4], c[5]};
+                std::memcpy(icov9 + 9 * m, full, sizeof full);
+            }
+        }
+        ++m;
+    }
+    *n_cells = m;
+    return WAVECU_OK;
+}
+
+int wavecu_ndt_derivatives(wavecu_ndt *w, const double pose6[6], const float T16[16], double *score, double g6[6],
+                           double H36[36]) {
+    if (!w || !pose6 || !T16 || !score || !g6 || !H36) return WAVECU_ERR_ARG;
+    NdtHandle &h = w->h;
+    WCU_CHECK(cudaSetDevice(h.device));
+    if (h.grid_dirty || h.clamped_res() != h.resolution) {
+        const int rc = h.build_grid();
+        if (rc) return rc;
+    }
+    *score = 0;
+    for (int i = 0; i < 6; ++i) g6[i] = 0;
+    for (int i = 0; i < 36; ++i) H36[i] = 0;
+    if (!h.grid_ok || !h.n_src) return WAVECU_OK;
+    const double o = 0.55, c1 = 10 * (1 - o), c2 = o / std::pow((double) h.resolution, 3), d3 = -std::log(c2);
+    const double gd1 = -std::log(c1 + c2) - d3;
+    const double gd2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / gd1);
+    return h.derivatives(pose6, T16, gd1, gd2, true, score, g6, H36);
+}
+
+int wavecu_ndt_stats(wavecu_ndt *w, long long *kernel_launches, long long *derivative_passes, int *n_cells) {
+    if (!w) return WAVECU_ERR_ARG;
+    if (kernel_launches) *kernel_launches = w->h.launches + w->h.vox.launches;
+    if (derivative_passes) *derivative_passes = w->h.derivative_passes;
+    if (n_cells) *n_cells = w->h.n_leaves;
+    return WAVECU_OK;
+}
+
+}  // extern "C"

@@ -13,12 +13,6 @@ namespace wavecu {
 
 namespace {
 
-struct GridDesc {
-    float inv;
-    int min_b[3];
-    int mul[3];
-};
-
 __global__ void voxel_key_kernel(const float4 *__restrict__ in, size_t n, GridDesc g, unsigned *keys, unsigned *vals) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -45,12 +39,11 @@ __global__ void voxel_head_kernel(const unsigned *__restrict__ keys, size_t n, i
 // one thread per voxel: fp32 sums in ascending cloud index (the sort is stable), centroid = sum / n
 __global__ void voxel_centroid_kernel(const float4 *__restrict__ in, const unsigned *__restrict__ keys,
                                       const unsigned *__restrict__ vals, const int *__restrict__ pos, size_t n,
-                                      float4 *out, int *total) {
+                                      float4 *out) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned k = keys[i];
     const bool head = (k != 0xffffffffu) && (i == 0 || keys[i - 1] != k);
-    if (i == n - 1) *total = pos[i] + (head ? 1 : 0);  // pos is the exclusive scan of the head flags
     if (!head) return;
     float sx = 0.f, sy = 0.f, sz = 0.f;
     size_t j = i;
@@ -62,6 +55,14 @@ __global__ void voxel_centroid_kernel(const float4 *__restrict__ in, const unsig
     }
     const float cnt = (float) (j - i);
     out[pos[i]] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 1.0f);
+}
+
+// pos is the exclusive scan of the head flags: total = pos[n-1] + head(n-1)
+__global__ void voxel_count_kernel(const unsigned *__restrict__ keys, const int *__restrict__ pos, size_t n, int *total) {
+    if (threadIdx.x != 0) return;
+    const unsigned k = keys[n - 1];
+    const bool head = (k != 0xffffffffu) && (n == 1 || keys[n - 2] != k);
+    *total = pos[n - 1] + (head ? 1 : 0);
 }
 
 __global__ void affine3d_kernel(float4 *cloud, size_t n, double m00, double m01, double m02, double m03, double m10,
@@ -116,9 +117,10 @@ int VoxelWork::reserve(size_t n) {
     return WAVECU_OK;
 }
 
-int VoxelWork::filter(const float4 *d_in, size_t n, float leaf, float4 *d_out, size_t *n_out, int *filtered) {
-    *n_out = 0;
-    if (filtered) *filtered = 1;
+int VoxelWork::prepare(const float4 *d_in, size_t n, float leaf, int *status) {
+    *status = -1;
+    n_voxels = 0;
+    n_sorted = n;
     if (n == 0) return WAVECU_OK;
     int rc = reserve(n);
     if (rc) return rc;
@@ -133,7 +135,7 @@ int VoxelWork::filter(const float4 *d_in, size_t n, float leaf, float4 *d_out, s
         memcpy(&f, &b, 4);
         return f;
     };
-    if (h_bbox[6] == 0) return WAVECU_OK;  // no finite point: empty output
+    if (h_bbox[6] == 0) return WAVECU_OK;  // no finite point
     float mn[3], mx[3];
     for (int d = 0; d < 3; ++d) {
         mn[d] = decode(h_bbox[d]);
@@ -144,38 +146,57 @@ int VoxelWork::filter(const float4 *d_in, size_t n, float leaf, float4 *d_out, s
     const int64_t dy = static_cast<int64_t>((mx[1] - mn[1]) * inv) + 1;
     const int64_t dz = static_cast<int64_t>((mx[2] - mn[2]) * inv) + 1;
     if ((dx * dy * dz) > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) {
-        // "Leaf size is too small for the input dataset. Integer indices would overflow.": output = input
-        if (d_out != d_in) WCU_CHECK(cudaMemcpyAsync(d_out, d_in, n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
-        *n_out = n;
-        if (filtered) *filtered = 0;
+        *status = 0;  // "Leaf size is too small for the input dataset. Integer indices would overflow."
         return WAVECU_OK;
     }
     GridDesc g;
     g.inv = inv;
-    int div_b[3];
     for (int d = 0; d < 3; ++d) {
         g.min_b[d] = static_cast<int>(std::floor(mn[d] * inv));
-        div_b[d] = static_cast<int>(std::floor(mx[d] * inv)) - g.min_b[d] + 1;
+        g.div_b[d] = static_cast<int>(std::floor(mx[d] * inv)) - g.min_b[d] + 1;
     }
     g.mul[0] = 1;
-    g.mul[1] = div_b[0];
-    g.mul[2] = div_b[0] * div_b[1];
-    const unsigned grid = (unsigned) ((n + 255) / 256);
-    voxel_key_kernel<<<grid, 256, 0, stream>>>(d_in, n, g, d_keys, d_vals);
+    g.mul[1] = g.div_b[0];
+    g.mul[2] = g.div_b[0] * g.div_b[1];
+    grid = g;
+    const unsigned blocks = (unsigned) ((n + 255) / 256);
+    voxel_key_kernel<<<blocks, 256, 0, stream>>>(d_in, n, g, d_keys, d_vals);
     cub::DoubleBuffer<unsigned> kb(d_keys, d_keys_alt), vb(d_vals, d_vals_alt);
     size_t need = tmp_bytes;
     WCU_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, need, kb, vb, (int) n, 0, 32, stream));
     if (kb.Current() != d_keys) std::swap(d_keys, d_keys_alt);
     if (vb.Current() != d_vals) std::swap(d_vals, d_vals_alt);
-    voxel_head_kernel<<<grid, 256, 0, stream>>>(d_keys, n, d_pos);
+    voxel_head_kernel<<<blocks, 256, 0, stream>>>(d_keys, n, d_pos);
     need = tmp_bytes;
     WCU_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp, need, d_pos, d_pos, (int) n, stream));
-    voxel_centroid_kernel<<<grid, 256, 0, stream>>>(d_in, d_keys, d_vals, d_pos, n, d_out, d_pos + n);
+    voxel_count_kernel<<<1, 32, 0, stream>>>(d_keys, d_pos, n, d_pos + n);
     launches += 3 + 6 + 2;
     WCU_CHECK(cudaMemcpyAsync(h_count, d_pos + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
     WCU_CHECK(cudaStreamSynchronize(stream));
     WCU_CHECK(cudaGetLastError());
-    *n_out = (size_t) *h_count;
+    n_voxels = *h_count;
+    *status = 1;
+    return WAVECU_OK;
+}
+
+int VoxelWork::filter(const float4 *d_in, size_t n, float leaf, float4 *d_out, size_t *n_out, int *filtered) {
+    *n_out = 0;
+    if (filtered) *filtered = 1;
+    if (n == 0) return WAVECU_OK;
+    int status = 0;
+    int rc = prepare(d_in, n, leaf, &status);
+    if (rc) return rc;
+    if (status < 0) return WAVECU_OK;  // no finite point: empty output
+    if (status == 0) {                 // overflow rule: output = input
+        if (d_out != d_in) WCU_CHECK(cudaMemcpyAsync(d_out, d_in, n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        *n_out = n;
+        if (filtered) *filtered = 0;
+        return WAVECU_OK;
+    }
+    voxel_centroid_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(d_in, d_keys, d_vals, d_pos, n, d_out);
+    ++launches;
+    WCU_CHECK(cudaGetLastError());
+    *n_out = (size_t) n_voxels;
     return WAVECU_OK;
 }
 

@@ -6,6 +6,14 @@
 
 namespace wavecu {
 
+// voxel indexing of pcl::VoxelGrid / VoxelGridCovariance: ijk = (int)(floor(p * inv) - (float) min_b)
+struct GridDesc {
+    float inv;
+    int min_b[3];
+    int div_b[3];
+    int mul[3];
+};
+
 struct VoxelWork {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -18,7 +26,16 @@ struct VoxelWork {
     int *h_count = nullptr;      // pinned
     long long launches = 0;
 
+    GridDesc grid{};             // of the last prepare()
+    size_t n_sorted = 0;         // points of the last prepare()
+    int n_voxels = 0;            // occupied voxels of the last prepare()
+
     int reserve(size_t n);
+    // bbox + voxel keys + stable sort + head flags + exclusive scan.  Afterwards d_keys/d_vals hold
+    // the (voxel index, cloud index) pairs in ascending voxel order (cloud order inside a voxel) and
+    // d_pos[i] the output slot of the voxel that sorted element i belongs to / starts.
+    // *status: 1 ok, 0 grid would overflow int32 (PCL passes the input through), -1 no finite point.
+    int prepare(const float4 *d_in, size_t n, float leaf, int *status);
     // out must have room for n points; *n_out receives the output size; *filtered = 0 when the
     // grid would overflow int32 and PCL copies the input through unchanged.
     int filter(const float4 *d_in, size_t n, float leaf, float4 *d_out, size_t *n_out, int *filtered);

@@ -219,6 +219,95 @@ class ICPMatcher(Matcher):
         return {k: getattr(s, k) for k, _ in capi.StatsC._fields_}
 
 
+@dataclasses.dataclass
+class NDTMatcherParams:
+    """wave::NDTMatcherParams, defaults from ndt.hpp:37-41 (step_size is an int in the reference)."""
+    step_size: int = 3
+    max_iter: int = 100
+    t_eps: float = 1e-8
+    res: float = 5.0
+    min_res: float = 0.05
+
+    def to_c(self) -> capi.NdtParamsC:
+        return capi.NdtParamsC(int(self.step_size), self.max_iter, self.t_eps, self.res)
+
+
+class NDTMatcher(Matcher):
+    """wave::NDTMatcher (ndt.hpp:44-80, src/ndt.cpp:18-65) on the GPU."""
+
+    def __init__(self, params: NDTMatcherParams | None = None, device: int = 0, stream: int | None = None):
+        self.params = dataclasses.replace(params) if params is not None else NDTMatcherParams()
+        if self.params.res < self.params.min_res:  # src/ndt.cpp:23-26
+            print("[ERROR] Invalid resolution given, using minimum")
+            self.params.res = self.params.min_res
+        super().__init__(self.params.res)
+        self._L = capi.lib()
+        self._h = C.c_void_p()
+        prm = self.params.to_c()
+        capi.check(self._L.wavecu_ndt_create(C.byref(prm), device, C.c_void_p(stream or 0), C.byref(self._h)))
+        self.converged = False
+        self.iterations = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.wavecu_ndt_destroy(h)
+            self._h = None
+
+    def setRef(self, ref):
+        a = _xyzw(ref)
+        capi.check(self._L.wavecu_ndt_set_source(self._h, _f(a), a.shape[0]))
+
+    def setTarget(self, target):
+        a = _xyzw(target)
+        capi.check(self._L.wavecu_ndt_set_target(self._h, _f(a), a.shape[0]))
+
+    def setRefDevice(self, ptr: int, n: int):
+        capi.check(self._L.wavecu_ndt_set_source_device(self._h, C.c_void_p(ptr), n))
+
+    def setTargetDevice(self, ptr: int, n: int):
+        capi.check(self._L.wavecu_ndt_set_target_device(self._h, C.c_void_p(ptr), n))
+
+    def match(self) -> bool:
+        prm = self.params.to_c()
+        capi.check(self._L.wavecu_ndt_set_params(self._h, C.byref(prm)))
+        T = np.empty(16, dtype=np.float64)
+        conv, iters = C.c_int(), C.c_int()
+        capi.check(self._L.wavecu_ndt_match(self._h, _d(T), C.byref(conv), C.byref(iters)))
+        self.converged, self.iterations = bool(conv.value), iters.value
+        if self.converged:
+            self.result = T.reshape(4, 4).copy()
+            return True
+        return False
+
+    def grid(self):
+        """(voxel index, count, fp32 centroid, fp64 mean, fp64 inverse covariance) of every cell."""
+        prm = self.params.to_c()
+        capi.check(self._L.wavecu_ndt_set_params(self._h, C.byref(prm)))
+        n = C.c_int()
+        capi.check(self._L.wavecu_ndt_grid(self._h, C.byref(n), None, None, None, None, None, 0))
+        m = n.value
+        voxel, count = np.empty(m, np.int32), np.empty(m, np.int32)
+        cen, mean, icov = np.empty((m, 3), np.float32), np.empty((m, 3), np.float64), np.empty((m, 9), np.float64)
+        capi.check(self._L.wavecu_ndt_grid(self._h, C.byref(n), _i(voxel), _i(count), _f(cen), _d(mean), _d(icov), m))
+        return voxel, count, cen, mean, icov.reshape(m, 3, 3)
+
+    def derivatives(self, pose, T):
+        prm = self.params.to_c()
+        capi.check(self._L.wavecu_ndt_set_params(self._h, C.byref(prm)))
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        T = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        score = C.c_double()
+        g, H = np.empty(6, np.float64), np.empty(36, np.float64)
+        capi.check(self._L.wavecu_ndt_derivatives(self._h, _d(pose), _f(T), C.byref(score), _d(g), _d(H)))
+        return score.value, g, H.reshape(6, 6)
+
+    def stats(self) -> dict:
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_int()
+        capi.check(self._L.wavecu_ndt_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"kernel_launches": a.value, "derivative_passes": b.value, "n_cells": c.value}
+
+
 def voxel_grid(cloud, leaf: float, device: int = 0):
     """pcl::VoxelGrid<pcl::PointXYZ>::filter on the GPU; returns (xyzw, filtered)."""
     a = _xyzw(cloud)

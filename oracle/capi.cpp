@@ -201,3 +201,76 @@ int wo_estimate_lum_old(const float *aligned, size_t n_src, const float *target,
 }
 
 }  // extern "C"
+
+// ---- NDT ------------------------------------------------------------------------------------------
+#include "ndt.hpp"
+
+extern "C" {
+
+struct wo_ndt_params_c {
+    int step_size;
+    int max_iter;
+    double t_eps;
+    float res;
+};
+
+// out: T16 (fp32 final transform), pose6, converged, iterations, n_voxels, score; trace arrays need
+// room for max_iter + 2 entries
+void wo_ndt_align(const float *src, size_t n_src, const float *tgt, size_t n_tgt, const wo_ndt_params_c *p, float *T16,
+                  double *pose6, int *converged, int *iterations, int *n_voxels, double *score, double *step_trace,
+                  int *n_trace) {
+    NdtParams prm;
+    prm.step_size = p->step_size;
+    prm.max_iter = p->max_iter;
+    prm.t_eps = p->t_eps;
+    prm.res = p->res;
+    NdtResult r;
+    ndt_align(src, n_src, tgt, n_tgt, prm, r);
+    std::memcpy(T16, r.final_T, sizeof r.final_T);
+    std::memcpy(pose6, r.pose, sizeof r.pose);
+    *converged = r.converged;
+    *iterations = r.iterations;
+    *n_voxels = r.n_voxels;
+    *score = r.score;
+    *n_trace = (int) r.step_trace.size();
+    for (size_t i = 0; i < r.step_trace.size(); ++i) step_trace[i] = r.step_trace[i];
+}
+
+// voxel statistics of the target grid: returns the number of leaves; arrays sized for n points
+size_t wo_ndt_grid(const float *tgt, size_t n, float res, int *voxel, int *count, float *centroid3, double *mean3,
+                   double *icov9) {
+    NdtGrid g;
+    g.build(tgt, n, res);
+    for (size_t i = 0; i < g.leaves.size(); ++i) {
+        voxel[i] = g.leaves[i].voxel;
+        count[i] = g.leaves[i].n;
+        for (int d = 0; d < 3; ++d) {
+            centroid3[3 * i + d] = g.leaves[i].centroid[d];
+            mean3[3 * i + d] = g.leaves[i].mean[d];
+        }
+        for (int d = 0; d < 9; ++d) icov9[9 * i + d] = g.leaves[i].icov[d];
+    }
+    return g.leaves.size();
+}
+
+// one computeDerivatives pass at pose p (source transformed by the fp32 pose matrix)
+double wo_ndt_derivatives(const float *src, size_t n_src, const float *tgt, size_t n_tgt, float res, const double *pose6,
+                          const float *T16, double *g6, double *H36) {
+    NdtGrid grid;
+    grid.build(tgt, n_tgt, res);
+    KdTree tree(grid.centroids.data(), grid.leaves.size(), 4);
+    std::vector<float> trans(4 * n_src);
+    for (size_t i = 0; i < n_src; ++i) {
+        const float x = src[4 * i], y = src[4 * i + 1], z = src[4 * i + 2];
+        trans[4 * i + 0] = T16[0] * x + T16[1] * y + T16[2] * z + T16[3];
+        trans[4 * i + 1] = T16[4] * x + T16[5] * y + T16[6] * z + T16[7];
+        trans[4 * i + 2] = T16[8] * x + T16[9] * y + T16[10] * z + T16[11];
+        trans[4 * i + 3] = 1.f;
+    }
+    const double o = 0.55, c1 = 10 * (1 - o), c2 = o / std::pow((double) res, 3), d3 = -std::log(c2);
+    const double d1 = -std::log(c1 + c2) - d3;
+    const double d2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / d1);
+    return ndt_derivatives(grid, tree, src, trans.data(), n_src, pose6, res, d1, d2, true, g6, H36);
+}
+
+}  // extern "C"

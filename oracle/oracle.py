@@ -301,3 +301,60 @@ def estimate_lum_old(aligned, target, max_corr, sum_mode=SUM_EXACT, k_quad: int 
     ok = lib().wo_estimate_lum_old(_f(a), a.shape[0], _f(t), t.shape[0], max_corr, sum_mode, k_quad - 2, k_quad - 4,
                                    _d(info), nn_threads)
     return info.reshape(6, 6), bool(ok)
+
+
+# ---- NDT (oracle/ndt.cpp) -------------------------------------------------------------------------
+class NdtParamsC(C.Structure):
+    _fields_ = [("step_size", C.c_int), ("max_iter", C.c_int), ("t_eps", C.c_double), ("res", C.c_float)]
+
+
+class NdtResult:
+    pass
+
+
+def ndt_align(source, target, *, step_size=3, max_iter=100, t_eps=1e-8, res=5.0) -> NdtResult:
+    """pcl::NormalDistributionsTransform::align as NDTMatcher drives it (src/ndt.cpp:18-65)."""
+    s, t = xyzw(source), xyzw(target)
+    L = lib()
+    L.wo_ndt_align.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, C.POINTER(NdtParamsC), _fp, _dp, _ip, _ip, _ip, _dp,
+                               _dp, _ip]
+    prm = NdtParamsC(step_size, max_iter, t_eps, res)
+    T = np.empty(16, dtype=np.float32)
+    pose = np.empty(6, dtype=np.float64)
+    conv, iters, nv, ntr = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    score = C.c_double()
+    trace = np.empty(max_iter + 4, dtype=np.float64)
+    L.wo_ndt_align(_f(s), s.shape[0], _f(t), t.shape[0], C.byref(prm), _f(T), _d(pose), C.byref(conv), C.byref(iters),
+                   C.byref(nv), C.byref(score), _d(trace), C.byref(ntr))
+    r = NdtResult()
+    r.T, r.pose, r.converged, r.iterations = T.reshape(4, 4), pose, bool(conv.value), iters.value
+    r.n_voxels, r.score, r.steps = nv.value, score.value, trace[:ntr.value].copy()
+    return r
+
+
+def ndt_grid(target, res):
+    t = xyzw(target)
+    n = t.shape[0]
+    L = lib()
+    L.wo_ndt_grid.restype = C.c_size_t
+    L.wo_ndt_grid.argtypes = [_fp, C.c_size_t, C.c_float, _ip, _ip, _fp, _dp, _dp]
+    voxel = np.empty(n, np.int32)
+    count = np.empty(n, np.int32)
+    cen = np.empty((n, 3), np.float32)
+    mean = np.empty((n, 3), np.float64)
+    icov = np.empty((n, 9), np.float64)
+    m = L.wo_ndt_grid(_f(t), n, res, _i(voxel), _i(count), _f(cen), _d(mean), _d(icov))
+    return voxel[:m].copy(), count[:m].copy(), cen[:m].copy(), mean[:m].copy(), icov[:m].reshape(m, 3, 3).copy()
+
+
+def ndt_derivatives(source, target, res, pose, T):
+    s, t = xyzw(source), xyzw(target)
+    L = lib()
+    L.wo_ndt_derivatives.restype = C.c_double
+    L.wo_ndt_derivatives.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, C.c_float, _dp, _fp, _dp, _dp]
+    pose = np.ascontiguousarray(pose, dtype=np.float64)
+    T = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+    g = np.empty(6, np.float64)
+    H = np.empty(36, np.float64)
+    score = L.wo_ndt_derivatives(_f(s), s.shape[0], _f(t), t.shape[0], res, _d(pose), _f(T), _d(g), _d(H))
+    return score, g, H.reshape(6, 6)
