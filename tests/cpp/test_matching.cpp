@@ -14,6 +14,7 @@
 
 #include "wave/matching/icp.hpp"
 #include "wave/matching/multi_matcher.hpp"
+#include "wave/matching/ndt.hpp"
 
 using namespace wave;
 
@@ -166,6 +167,25 @@ int main(int argc, char **argv) {
         for (bool s : seen) all = all && s;
         EXPECT(got == 8 && all, "simultaneousmatching");
         std::printf("%-18s results=%d\n", "multimatcher", got);
+    }
+    if (argc >= 4) {  // NDTTests (tests/ndt_tests.cpp): initialization, fullResNullMatch, nullDisplacement
+        const std::string ndt_config = argv[3];
+        const float ndt_threshold = 0.12f;  // tests/ndt_tests.cpp:37
+        { NDTMatcher matcher{NDTMatcherParams()}; }
+        const float res_cases[] = {-1.f /* keep the yaml's 0.05 */, 0.1f};
+        for (float r : res_cases) {
+            Affine3 perturb = Affine3::Identity();
+            NDTMatcherParams params(ndt_config);
+            if (r > 0) params.res = r;
+            NDTMatcher matcher(params);
+            PCLPointCloudPtr target = transformed(ref, perturb);
+            matcher.setup(ref, target);
+            const bool match_success = matcher.match();
+            const double diff = (matcher.getResult().matrix() - perturb.matrix()).norm();
+            EXPECT(match_success, "ndt_null");
+            EXPECT(diff < ndt_threshold, "ndt_null");
+            std::printf("%-18s res=%.2f match=%d diff=%.3e\n", "ndt_null", matcher.getRes(), (int) match_success, diff);
+        }
     }
     std::printf("%s (%d failures)\n", failures ? "FAILED" : "PASSED", failures);
     return failures;

@@ -1,0 +1,63 @@
+"""CPU tests (-m "not gpu") of the NDT oracle (oracle/ndt.cpp): analytic derivatives against finite
+differences, the reference's null-displacement cases, and the voxel statistics against numpy."""
+import numpy as np
+
+from conftest import pcl_transform
+
+
+def pose_matrix(p):
+    rx, ry, rz = (np.float32(v) for v in p[3:])
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    T = np.eye(4, dtype=np.float32)
+    T[0, :3] = [cy * cz, -cy * sz, sy]
+    T[1, :3] = [sx * sy * cz + cx * sz, -sx * sy * sz + cx * cz, -sx * cy]
+    T[2, :3] = [-cx * sy * cz + sx * sz, cx * sy * sz + sx * cz, cx * cy]
+    T[:3, 3] = np.asarray(p[:3], dtype=np.float32)
+    return T
+
+
+def test_ndt_cells_against_numpy(oracle, testscan):
+    res = 1.0
+    voxel, count, cen, mean, icov = oracle.ndt_grid(testscan, res)
+    assert (count >= 6).all() and (np.diff(voxel) > 0).all()
+    inv = np.float32(1.0) / np.float32(res)
+    ijk = np.floor(testscan * inv) - np.floor(testscan.min(0) * inv)
+    div = (np.floor(testscan.max(0) * inv) - np.floor(testscan.min(0) * inv) + 1).astype(np.int64)
+    idx = (ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]).astype(np.int64)
+    for k in (0, len(voxel) // 2, len(voxel) - 1):
+        pts = testscan[idx == voxel[k]].astype(np.float64)
+        assert len(pts) == count[k]
+        assert np.allclose(pts.mean(0), mean[k], atol=1e-9)
+        cov = np.cov(pts.T, bias=True) * (len(pts) - 1.0) / len(pts)   # PCL's single-pass formula
+        ev, V = np.linalg.eigh(cov)
+        ev = np.maximum(ev, 0.01 * ev[2])
+        assert np.allclose(np.linalg.inv(V @ np.diag(ev) @ V.T), icov[k], rtol=1e-6, atol=1e-6 * np.abs(icov[k]).max())
+
+
+def test_ndt_gradient_matches_finite_differences(oracle, testscan):
+    T0 = np.eye(4)
+    T0[0, 3] = 0.2
+    tgt = pcl_transform(testscan, T0)
+    src = testscan[::5]
+    p0 = np.array([0.05, 0.02, -0.01, 0.01, -0.02, 0.015])
+    s, g, H = oracle.ndt_derivatives(src, tgt, 1.0, p0, pose_matrix(p0))
+    assert np.allclose(H, H.T, rtol=1e-9, atol=1e-6 * np.abs(H).max())
+    h = 1e-4
+    for i in range(3):  # translations: the fp32 pose matrix is exact enough for a clean difference
+        pp, pm = p0.copy(), p0.copy()
+        pp[i] += h
+        pm[i] -= h
+        sp, gp, _ = oracle.ndt_derivatives(src, tgt, 1.0, pp, pose_matrix(pp))
+        sm, gm, _ = oracle.ndt_derivatives(src, tgt, 1.0, pm, pose_matrix(pm))
+        assert abs((sp - sm) / (2 * h) - g[i]) < 0.02 * np.abs(g).max()
+        assert np.abs((gp - gm) / (2 * h) - H[:, i])[:3].max() < 0.02 * np.abs(H[:3, :3]).max()
+
+
+def test_ndt_reference_null_case(oracle, testscan):
+    """nullDisplacement (tests/ndt_tests.cpp:64-82): identical clouds, res 0.1 -> ||T - I||_F < 0.12.
+    With t_eps = 1e-8 PCL never meets its step criterion here and stops on the iteration cap."""
+    r = oracle.ndt_align(testscan, testscan.copy(), res=0.1)
+    assert r.converged and r.iterations == 102
+    assert np.linalg.norm(r.T - np.eye(4)) < 0.12
+    assert np.linalg.norm(r.T - np.eye(4)) < 1e-3
+    assert not oracle.ndt_align(np.zeros((0, 3), np.float32), testscan, res=1.0).converged
