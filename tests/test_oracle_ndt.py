@@ -34,23 +34,33 @@ def test_ndt_cells_against_numpy(oracle, testscan):
         assert np.allclose(np.linalg.inv(V @ np.diag(ev) @ V.T), icov[k], rtol=1e-6, atol=1e-6 * np.abs(icov[k]).max())
 
 
-def test_ndt_gradient_matches_finite_differences(oracle, testscan):
+def test_ndt_derivatives_match_finite_differences(oracle, testscan):
+    """The score is only piecewise smooth (a point entering or leaving a cell's radius moves it by a
+    finite amount), so the differences are taken where those jumps are small against the slope."""
     T0 = np.eye(4)
     T0[0, 3] = 0.2
     tgt = pcl_transform(testscan, T0)
     src = testscan[::5]
-    p0 = np.array([0.05, 0.02, -0.01, 0.01, -0.02, 0.015])
-    s, g, H = oracle.ndt_derivatives(src, tgt, 1.0, p0, pose_matrix(p0))
-    assert np.allclose(H, H.T, rtol=1e-9, atol=1e-6 * np.abs(H).max())
     h = 1e-4
-    for i in range(3):  # translations: the fp32 pose matrix is exact enough for a clean difference
+    p0 = np.zeros(6)
+    s, g, H = oracle.ndt_derivatives(src, tgt, 0.3, p0, pose_matrix(p0))
+    assert np.allclose(H, H.T, rtol=1e-9, atol=1e-6 * np.abs(H).max())
+    for i in range(3):  # d score / d translation
         pp, pm = p0.copy(), p0.copy()
         pp[i] += h
         pm[i] -= h
-        sp, gp, _ = oracle.ndt_derivatives(src, tgt, 1.0, pp, pose_matrix(pp))
-        sm, gm, _ = oracle.ndt_derivatives(src, tgt, 1.0, pm, pose_matrix(pm))
-        assert abs((sp - sm) / (2 * h) - g[i]) < 0.02 * np.abs(g).max()
-        assert np.abs((gp - gm) / (2 * h) - H[:, i])[:3].max() < 0.02 * np.abs(H[:3, :3]).max()
+        sp, _, _ = oracle.ndt_derivatives(src, tgt, 0.3, pp, pose_matrix(pp))
+        sm, _, _ = oracle.ndt_derivatives(src, tgt, 0.3, pm, pose_matrix(pm))
+        assert abs((sp - sm) / (2 * h) - g[i]) < 0.05 * np.abs(g[:3]).max()
+    p1 = np.array([0.05, 0.02, -0.01, 0.01, -0.02, 0.015])
+    _, g1, H1 = oracle.ndt_derivatives(src, tgt, 1.0, p1, pose_matrix(p1))
+    for i in range(3):  # d gradient / d translation against the analytic Hessian columns
+        pp, pm = p1.copy(), p1.copy()
+        pp[i] += 1e-5
+        pm[i] -= 1e-5
+        _, gp, _ = oracle.ndt_derivatives(src, tgt, 1.0, pp, pose_matrix(pp))
+        _, gm, _ = oracle.ndt_derivatives(src, tgt, 1.0, pm, pose_matrix(pm))
+        assert np.abs((gp - gm) / 2e-5 - H1[:, i]).max() < 0.02 * np.abs(H1[:, :3]).max()
 
 
 def test_ndt_reference_null_case(oracle, testscan):
