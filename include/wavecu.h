@@ -21,6 +21,8 @@
  *                                  src/icp_pcl_functions.cpp:67-80
  *   wavecu_voxel_grid              pcl::VoxelGrid::filter, src/icp.cpp:81-90,106-113,
  *                                  src/gicp.cpp:39-40,49-50
+ *   wavecu_gicp_*                  pcl::GeneralizedIterativeClosestPoint member + plumbing,
+ *                                  include/wave/matching/gicp.hpp:61, src/gicp.cpp:20-64
  *   wavecu_ndt_*                   pcl::NormalDistributionsTransform member + plumbing,
  *                                  include/wave/matching/ndt.hpp:72, src/ndt.cpp:18-65
  *
@@ -174,6 +176,37 @@ int wavecu_ndt_grid(wavecu_ndt *h, int *n_cells, int *voxel, int *count, float *
 int wavecu_ndt_derivatives(wavecu_ndt *h, const double pose6[6], const float T16[16], double *score, double g6[6],
                            double H36[36]);
 int wavecu_ndt_stats(wavecu_ndt *h, long long *kernel_launches, long long *derivative_passes, int *n_cells);
+
+/* ---- GICPMatcher (include/wave/matching/gicp.hpp:30-65, src/gicp.cpp:20-64) -------------------------
+ * Field-for-field mirror of wave::GICPMatcherParams (gicp.hpp:34-38). */
+typedef struct {
+    int corr_rand;   /* gicp.hpp:34, default 10 (k of the covariance neighbourhoods) */
+    int max_iter;    /* gicp.hpp:35, default 100 */
+    double r_eps;    /* gicp.hpp:36, default 1e-8 (rotation epsilon) */
+    double fit_eps;  /* gicp.hpp:37, default 1e-2 (passed to PCL but unused by GICP) */
+    float res;       /* gicp.hpp:38, default 0.1: voxel filter applied in setRef/setTarget; <= 0 none */
+} wavecu_gicp_params;
+
+void wavecu_gicp_default_params(wavecu_gicp_params *p);
+
+typedef struct wavecu_gicp wavecu_gicp;
+int wavecu_gicp_create(const wavecu_gicp_params *params, int device, void *stream, wavecu_gicp **out);
+int wavecu_gicp_destroy(wavecu_gicp *h);
+int wavecu_gicp_set_params(wavecu_gicp *h, const wavecu_gicp_params *params);
+/* GICPMatcher::setRef / setTarget (src/gicp.cpp:37-55): voxel-filter when res > 0, then
+ * gicp.setInputSource / setInputTarget */
+int wavecu_gicp_set_source(wavecu_gicp *h, const float *xyzw, size_t n);
+int wavecu_gicp_set_target(wavecu_gicp *h, const float *xyzw, size_t n);
+int wavecu_gicp_set_source_device(wavecu_gicp *h, const void *d_xyzw, size_t n);
+int wavecu_gicp_set_target_device(wavecu_gicp *h, const void *d_xyzw, size_t n);
+/* gicp.align + hasConverged + getFinalTransformation (src/gicp.cpp:57-64) */
+int wavecu_gicp_match(wavecu_gicp *h, double T_out[16], int *converged, int *iterations);
+/* Per-point covariances (which = 0 source, 1 target) in the order of the (filtered) cloud, 9 doubles
+ * each; covs9 may be NULL to query the size.  wavecu_gicp_cloud returns that (filtered) cloud. */
+int wavecu_gicp_covariances(wavecu_gicp *h, int which, double *covs9, size_t *n);
+int wavecu_gicp_cloud(wavecu_gicp *h, int which, float *xyzw, size_t *n);
+int wavecu_gicp_stats(wavecu_gicp *h, long long *kernel_launches, long long *evaluations,
+                      long long *inner_iterations, size_t *n_corr);
 
 /* pcl::VoxelGrid<pcl::PointXYZ>::filter (src/icp.cpp:81-90,106-113; src/gicp.cpp:39-40,49-50):
  * one centroid per occupied voxel in ascending voxel index; out_xyzw needs room for n points.

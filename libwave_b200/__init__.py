@@ -4,5 +4,6 @@ Product code: the CUDA library (csrc/, built to libwavecu.so behind include/wave
 host-side mirror of the reference's matcher interface (matching.py).  ``synth`` is the synthetic
 scan generator used by the tests and the bench.  Nothing here imports ``oracle/``.
 """
-from .matching import (EST_POINT_TO_PLANE, EST_SVD, INFO_CENSI, INFO_LUM, INFO_LUMOLD, ICPMatcher,  # noqa: F401
+from .matching import (EST_POINT_TO_PLANE, EST_SVD, INFO_CENSI, INFO_LUM, INFO_LUMOLD, GICPMatcher,  # noqa: F401
+                       GICPMatcherParams, ICPMatcher,
                        ICPMatcherParams, Matcher, NDTMatcher, NDTMatcherParams, NearestNeighbour, voxel_grid)

@@ -31,6 +31,12 @@ class NdtParamsC(C.Structure):
     _fields_ = [("step_size", C.c_int), ("max_iter", C.c_int), ("t_eps", C.c_double), ("res", C.c_float)]
 
 
+class GicpParamsC(C.Structure):
+    """wavecu_gicp_params == wave::GICPMatcherParams (gicp.hpp:34-38)."""
+    _fields_ = [("corr_rand", C.c_int), ("max_iter", C.c_int), ("r_eps", C.c_double), ("fit_eps", C.c_double),
+                ("res", C.c_float)]
+
+
 class StatsC(C.Structure):
     _fields_ = [("build_ms", C.c_double), ("iterate_ms", C.c_double), ("solve_ms", C.c_double),
                 ("total_ms", C.c_double), ("iterate_launches", C.c_longlong), ("kernel_launches", C.c_longlong),
@@ -78,6 +84,19 @@ SIGNATURES = {
     "wavecu_ndt_grid": (C.c_int, [_vp, _ip, _ip, _ip, _fp, _dp, _dp, C.c_int]),
     "wavecu_ndt_derivatives": (C.c_int, [_vp, _dp, _fp, _dp, _dp, _dp]),
     "wavecu_ndt_stats": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _ip]),
+    "wavecu_gicp_default_params": (None, [C.POINTER(GicpParamsC)]),
+    "wavecu_gicp_create": (C.c_int, [C.POINTER(GicpParamsC), C.c_int, _vp, C.POINTER(_vp)]),
+    "wavecu_gicp_destroy": (C.c_int, [_vp]),
+    "wavecu_gicp_set_params": (C.c_int, [_vp, C.POINTER(GicpParamsC)]),
+    "wavecu_gicp_set_source": (C.c_int, [_vp, _fp, _sz]),
+    "wavecu_gicp_set_target": (C.c_int, [_vp, _fp, _sz]),
+    "wavecu_gicp_set_source_device": (C.c_int, [_vp, _vp, _sz]),
+    "wavecu_gicp_set_target_device": (C.c_int, [_vp, _vp, _sz]),
+    "wavecu_gicp_match": (C.c_int, [_vp, _dp, _ip, _ip]),
+    "wavecu_gicp_covariances": (C.c_int, [_vp, C.c_int, _dp, _szp]),
+    "wavecu_gicp_cloud": (C.c_int, [_vp, C.c_int, _fp, _szp]),
+    "wavecu_gicp_stats": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                    _szp]),
     "wavecu_voxel_grid": (C.c_int, [C.c_int, _fp, _sz, C.c_float, _fp, _szp, _ip]),
     "wavecu_last_error": (C.c_char_p, []),
     "wavecu_device_count": (C.c_int, []),

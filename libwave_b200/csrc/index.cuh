@@ -213,6 +213,92 @@ inline NnIndex TargetIndex::index() const {
     return ix;
 }
 
+// Exact k-NN (k <= kMaxKnn) under l2_simple, ordered by (distance, original index) - the order
+// FLANN's sorted k-NN result set yields up to exact ties.  d[]/idx[]/pos[] are kept sorted; a
+// subtree is skipped only when its box bound exceeds the current k-th distance.
+constexpr int kMaxKnn = 32;
+
+struct KnnList {
+    float d[kMaxKnn];
+    int idx[kMaxKnn];
+    int pos[kMaxKnn];
+    int k;
+    __device__ __forceinline__ void init(int k_) {
+        k = k_;
+        for (int i = 0; i < k_; ++i) {
+            d[i] = INFINITY;
+            idx[i] = 0x7fffffff;
+            pos[i] = -1;
+        }
+    }
+    __device__ __forceinline__ float worst() const { return d[k - 1]; }
+    __device__ __forceinline__ void offer(float dist, int index, int position) {
+        if (!(dist < d[k - 1] || (dist == d[k - 1] && index < idx[k - 1]))) return;
+        int p = k - 1;
+        while (p > 0 && (d[p - 1] > dist || (d[p - 1] == dist && idx[p - 1] > index))) {
+            d[p] = d[p - 1];
+            idx[p] = idx[p - 1];
+            pos[p] = pos[p - 1];
+            --p;
+        }
+        d[p] = dist;
+        idx[p] = index;
+        pos[p] = position;
+    }
+};
+
+__device__ __forceinline__ void knn_search(float qx, float qy, float qz, const NnIndex &ix, KnnList &out) {
+    const float4 rlo = __ldg(&ix.root->lo), rhi = __ldg(&ix.root->hi);
+    if (__float_as_int(rhi.w) <= 0) return;
+    int link = __float_as_int(rlo.w);
+    int stack_link[kStackDepth];
+    float stack_d[kStackDepth];
+    int sp = 0;
+    for (;;) {
+        while (link >= 0) {
+            const float4 a = __ldg(&ix.nodes[link].lo0), b = __ldg(&ix.nodes[link].hi0);
+            const float4 c = __ldg(&ix.nodes[link].lo1), d = __ldg(&ix.nodes[link].hi1);
+            const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
+            const bool right_first = d1 < d0;
+            const float dn = right_first ? d1 : d0, df = right_first ? d0 : d1;
+            const int ln = __float_as_int(right_first ? c.w : a.w), lf = __float_as_int(right_first ? a.w : c.w);
+            if (dn <= out.worst()) {
+                if (df <= out.worst()) {
+                    stack_link[sp] = lf;
+                    stack_d[sp] = df;
+                    ++sp;
+                }
+                link = ln;
+            } else {
+                link = kLinkDone;
+                while (sp > 0) {
+                    --sp;
+                    if (stack_d[sp] <= out.worst()) {
+                        link = stack_link[sp];
+                        break;
+                    }
+                }
+            }
+        }
+        if (link == kLinkDone) return;
+        {
+            const int start = leaf_start(link), cnt = leaf_count(link);
+            for (int k = 0; k < cnt; ++k) {
+                const float4 p = __ldg(ix.pts + start + k);
+                out.offer(l2_simple(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), start + k);
+            }
+        }
+        link = kLinkDone;
+        while (sp > 0) {
+            --sp;
+            if (stack_d[sp] <= out.worst()) {
+                link = stack_link[sp];
+                break;
+            }
+        }
+    }
+}
+
 // Exact 1-NN of (qx,qy,qz) under l2_simple with the lowest original index among exact ties.
 // best / best_idx / best_pos come in as the current bound (the max-correspondence threshold with
 // best_idx = INT_MAX and best_pos = -1, possibly improved by a warm-start candidate) and leave as

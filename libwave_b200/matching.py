@@ -220,6 +220,80 @@ class ICPMatcher(Matcher):
 
 
 @dataclasses.dataclass
+class GICPMatcherParams:
+    """wave::GICPMatcherParams, defaults from gicp.hpp:34-38."""
+    corr_rand: int = 10
+    max_iter: int = 100
+    r_eps: float = 1e-8
+    fit_eps: float = 1e-2
+    res: float = 0.1
+
+    def to_c(self) -> capi.GicpParamsC:
+        return capi.GicpParamsC(self.corr_rand, self.max_iter, self.r_eps, self.fit_eps, self.res)
+
+
+class GICPMatcher(Matcher):
+    """wave::GICPMatcher (gicp.hpp:41-65, src/gicp.cpp:20-64) on the GPU.  As in the reference the
+    voxel filter runs inside setRef / setTarget and the parameters are fixed at construction."""
+
+    def __init__(self, params: GICPMatcherParams | None = None, device: int = 0, stream: int | None = None):
+        self.params = dataclasses.replace(params) if params is not None else GICPMatcherParams()
+        super().__init__(self.params.res if self.params.res > 0 else -1.0)
+        self._L = capi.lib()
+        self._h = C.c_void_p()
+        prm = self.params.to_c()
+        capi.check(self._L.wavecu_gicp_create(C.byref(prm), device, C.c_void_p(stream or 0), C.byref(self._h)))
+        self.converged = False
+        self.iterations = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.wavecu_gicp_destroy(h)
+            self._h = None
+
+    def setRef(self, ref):
+        a = _xyzw(ref)
+        capi.check(self._L.wavecu_gicp_set_source(self._h, _f(a), a.shape[0]))
+
+    def setTarget(self, target):
+        a = _xyzw(target)
+        capi.check(self._L.wavecu_gicp_set_target(self._h, _f(a), a.shape[0]))
+
+    def setRefDevice(self, ptr: int, n: int):
+        capi.check(self._L.wavecu_gicp_set_source_device(self._h, C.c_void_p(ptr), n))
+
+    def setTargetDevice(self, ptr: int, n: int):
+        capi.check(self._L.wavecu_gicp_set_target_device(self._h, C.c_void_p(ptr), n))
+
+    def match(self) -> bool:
+        T = np.empty(16, dtype=np.float64)
+        conv, iters = C.c_int(), C.c_int()
+        capi.check(self._L.wavecu_gicp_match(self._h, _d(T), C.byref(conv), C.byref(iters)))
+        self.converged, self.iterations = bool(conv.value), iters.value
+        if self.converged:
+            self.result = T.reshape(4, 4).copy()
+            return True
+        return False
+
+    def covariances(self, which: int):
+        """(filtered cloud, per-point 3x3 covariances); which = 0 source, 1 target."""
+        n = C.c_size_t()
+        capi.check(self._L.wavecu_gicp_covariances(self._h, which, None, C.byref(n)))
+        covs = np.empty((n.value, 9), dtype=np.float64)
+        cloud = np.empty((n.value, 4), dtype=np.float32)
+        capi.check(self._L.wavecu_gicp_covariances(self._h, which, _d(covs), C.byref(n)))
+        capi.check(self._L.wavecu_gicp_cloud(self._h, which, _f(cloud), C.byref(n)))
+        return cloud, covs.reshape(-1, 3, 3)
+
+    def stats(self) -> dict:
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        n = C.c_size_t()
+        capi.check(self._L.wavecu_gicp_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return {"kernel_launches": a.value, "evaluations": b.value, "inner_iterations": c.value, "n_corr": n.value}
+
+
+@dataclasses.dataclass
 class NDTMatcherParams:
     """wave::NDTMatcherParams, defaults from ndt.hpp:37-41 (step_size is an int in the reference)."""
     step_size: int = 3

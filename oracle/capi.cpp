@@ -274,3 +274,36 @@ double wo_ndt_derivatives(const float *src, size_t n_src, const float *tgt, size
 }
 
 }  // extern "C"
+
+// ---- GICP -----------------------------------------------------------------------------------------
+#include "gicp.hpp"
+
+extern "C" {
+
+void wo_gicp_covariances(const float *cloud, size_t n, int k, double eps, double *covs9) {
+    KdTree tree(cloud, n, 4);
+    std::vector<double> c;
+    if (!gicp_covariances(cloud, n, tree, k, eps, c)) c.assign(9 * n, 0.0);
+    std::memcpy(covs9, c.data(), c.size() * sizeof(double));
+}
+
+void wo_gicp_align(const float *src, size_t n_src, const float *tgt, size_t n_tgt, int corr_rand, int max_iter,
+                   double r_eps, float *T16, int *converged, int *iterations, size_t *n_corr, long long *inner,
+                   long long *evals, double *delta_trace, int *n_trace) {
+    GicpParams prm;
+    prm.corr_rand = corr_rand;
+    prm.max_iter = max_iter;
+    prm.r_eps = r_eps;
+    GicpResult r;
+    gicp_align(src, n_src, tgt, n_tgt, prm, r);
+    std::memcpy(T16, r.final_T, sizeof r.final_T);
+    *converged = r.converged;
+    *iterations = r.iterations;
+    *n_corr = r.n_corr;
+    *inner = r.inner_iterations;
+    *evals = r.evaluations;
+    *n_trace = (int) r.delta_trace.size();
+    for (size_t i = 0; i < r.delta_trace.size(); ++i) delta_trace[i] = r.delta_trace[i];
+}
+
+}  // extern "C"

@@ -358,3 +358,37 @@ def ndt_derivatives(source, target, res, pose, T):
     H = np.empty(36, np.float64)
     score = L.wo_ndt_derivatives(_f(s), s.shape[0], _f(t), t.shape[0], res, _d(pose), _f(T), _d(g), _d(H))
     return score, g, H.reshape(6, 6)
+
+
+# ---- GICP (oracle/gicp.cpp) -----------------------------------------------------------------------
+class GicpResult:
+    pass
+
+
+def gicp_covariances(cloud, k=10, eps=1e-3):
+    c = xyzw(cloud)
+    L = lib()
+    L.wo_gicp_covariances.argtypes = [_fp, C.c_size_t, C.c_int, C.c_double, _dp]
+    out = np.empty((c.shape[0], 9), dtype=np.float64)
+    L.wo_gicp_covariances(_f(c), c.shape[0], k, eps, _d(out))
+    return out.reshape(-1, 3, 3)
+
+
+def gicp_align(source, target, *, corr_rand=10, max_iter=100, r_eps=1e-8) -> GicpResult:
+    """pcl::GeneralizedIterativeClosestPoint::align as GICPMatcher drives it (src/gicp.cpp:20-64);
+    voxel filtering (src/gicp.cpp:37-55) is the caller's job: pass voxel_grid() outputs."""
+    s, t = xyzw(source), xyzw(target)
+    L = lib()
+    L.wo_gicp_align.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, C.c_int, C.c_int, C.c_double, _fp, _ip, _ip,
+                                C.POINTER(C.c_size_t), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _dp, _ip]
+    T = np.empty(16, dtype=np.float32)
+    conv, iters, ntr = C.c_int(), C.c_int(), C.c_int()
+    nc = C.c_size_t()
+    inner, evals = C.c_longlong(), C.c_longlong()
+    trace = np.empty(max_iter + 4, dtype=np.float64)
+    L.wo_gicp_align(_f(s), s.shape[0], _f(t), t.shape[0], corr_rand, max_iter, r_eps, _f(T), C.byref(conv),
+                    C.byref(iters), C.byref(nc), C.byref(inner), C.byref(evals), _d(trace), C.byref(ntr))
+    r = GicpResult()
+    r.T, r.converged, r.iterations, r.n_corr = T.reshape(4, 4), bool(conv.value), iters.value, nc.value
+    r.inner_iterations, r.evaluations, r.delta = inner.value, evals.value, trace[:ntr.value].copy()
+    return r
