@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include "wave/matching/gicp.hpp"
 #include "wave/matching/icp.hpp"
 #include "wave/matching/multi_matcher.hpp"
 #include "wave/matching/ndt.hpp"
@@ -185,6 +186,26 @@ int main(int argc, char **argv) {
             EXPECT(match_success, "ndt_null");
             EXPECT(diff < ndt_threshold, "ndt_null");
             std::printf("%-18s res=%.2f match=%d diff=%.3e\n", "ndt_null", matcher.getRes(), (int) match_success, diff);
+        }
+    }
+    if (argc >= 5) {  // GICPTests (tests/gicp_tests.cpp): fullResNullMatch, nullDisplacement, smallDisplacement
+        const std::string gicp_config = argv[4];
+        { GICPMatcher matcher{GICPMatcherParams()}; }
+        struct GCase { const char *name; float res; double tx; };
+        const GCase gcases[] = {{"gicp_fullResNull", -1.f, 0.0}, {"gicp_nullDisp", 0.05f, 0.0}, {"gicp_smallDisp", 0.05f, 0.2}};
+        for (const GCase &c : gcases) {
+            Affine3 perturb = Affine3::Identity();
+            perturb.translation() << c.tx, 0, 0;
+            GICPMatcherParams params(gicp_config);
+            params.res = c.res;
+            GICPMatcher matcher(params);
+            PCLPointCloudPtr target = transformed(ref, perturb);
+            matcher.setup(ref, target);
+            const bool match_success = matcher.match();
+            const double diff = (matcher.getResult().matrix() - perturb.matrix()).norm();
+            EXPECT(match_success, c.name);
+            EXPECT(diff < threshold, c.name);
+            std::printf("%-18s match=%d diff=%.3e\n", c.name, (int) match_success, diff);
         }
     }
     std::printf("%s (%d failures)\n", failures ? "FAILED" : "PASSED", failures);

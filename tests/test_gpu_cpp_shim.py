@@ -17,7 +17,8 @@ def test_reference_gtest_cases_native():
     assert exe.exists()
     r = subprocess.run([str(exe), str(ROOT / "tests" / "golden" / "testscan_xyz.f32"),
                         str(ROOT / "tests" / "cpp" / "config" / "icp.yaml"),
-                        str(ROOT / "tests" / "cpp" / "config" / "ndt.yaml")], capture_output=True, text=True, timeout=900)
+                        str(ROOT / "tests" / "cpp" / "config" / "ndt.yaml"),
+                        str(ROOT / "tests" / "cpp" / "config" / "gicp.yaml")], capture_output=True, text=True, timeout=900)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "PASSED" in r.stdout
