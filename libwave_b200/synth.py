@@ -187,6 +187,29 @@ def scan_pair(n: int, scan_id: int | None = None, T_true=None, return_normals: b
     return (src, *out) if return_normals else (src, out)
 
 
+def scan_batch(n: int, count: int, first_id: int = 0, ids=None):
+    """`count` source scans of n points of the same scene from the sensor origin, differing only in
+    their range-noise seed (batch scan k: seed 1000 + k), plus the shared target ("map") scan taken
+    from T_true^-1 (seed 2).  One ray cast serves all sources, so a 256-scan batch costs seconds."""
+    rings, az = SIZES[n]
+    scene = make_scene()
+    elev = np.deg2rad(np.linspace(ELEV_DEG[0], ELEV_DEG[1], rings))
+    azs = 2.0 * np.pi * np.arange(az) / az
+    azg, elg = np.meshgrid(azs, elev, indexing="ij")
+    azg, elg = azg.ravel(), elg.ravel()
+    d_s = np.stack([np.cos(elg) * np.cos(azg), np.cos(elg) * np.sin(azg), np.sin(elg)], axis=1)
+    t, _ = _raycast(np.zeros(3), d_s, scene)
+    ok = np.isfinite(t) & (t <= MAX_RANGE)
+    t, d_s = t[ok], d_s[ok]
+    ids = list(range(first_id, first_id + count)) if ids is None else list(ids)
+    sources = []
+    for k in ids:
+        noise = np.random.Generator(np.random.PCG64(1000 + k)).normal(0.0, SIGMA, t.shape[0])
+        sources.append(((t + noise)[:, None] * d_s).astype(np.float32))
+    target = velodyne_scan(rings, az, np.linalg.inv(T_TRUE), TARGET_SEED, scene, n_points=n)
+    return sources, target
+
+
 def map_cloud(n_scans: int = 5, n_per_scan: int = 1_000_000, baseline: float = 4.0):
     """Union of n_scans scans along a baseline on x, all expressed in the frame of T_true^-1
     (the target frame of scan_pair) - the 5M-point NDT map of BASELINE.json config 4."""
