@@ -236,10 +236,6 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     have_result = false;
     const size_t n_src = src.n, n_tgt = tgt.cloud.n;
     const int max_iter = std::max(prm.max_iter, 1);
-    if (prm.estimator == WAVECU_EST_POINT_TO_PLANE && tgt.nrm_n != n_tgt) {
-        set_last_error("point-to-plane estimator needs target normals (wavecu_icp_set_target_normals)");
-        return WAVECU_ERR_STATE;
-    }
     stats = wavecu_stats{};
     const long long launches0 = src.launches + tgt.cloud.launches;
     cudaEvent_t e_begin = nullptr, e_built = nullptr, e_end = nullptr;
@@ -265,6 +261,11 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     if (rc) return rc;
     if (tgt.dirty) {
         rc = tgt.build();
+        if (rc) return rc;
+    }
+    if (prm.estimator == WAVECU_EST_POINT_TO_PLANE && tgt.nrm_n != n_tgt && !tgt.normals_estimated) {
+        // no normals from the caller: estimate them on the target's own tree (k = 10 neighbours)
+        rc = tgt.estimate_normals(10);
         if (rc) return rc;
     }
     // the working cloud is consumed by the iterations, so the source is re-sorted for every align

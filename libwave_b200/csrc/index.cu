@@ -5,6 +5,7 @@
 
 #include "../../include/wavecu.h"
 #include "index.cuh"
+#include "linalg.cuh"
 #include "voxel.cuh"
 
 namespace wavecu {
@@ -169,6 +170,52 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
     }
 }
 
+// Surface normal of every Morton-sorted target point from its k nearest neighbours (itself
+// included): fp64 covariance, 3x3 Jacobi, direction of least variance, flipped towards the sensor
+// origin (pcl::flipNormalTowardsViewpoint with the default viewpoint).  Used by the point-to-plane
+// estimator when the caller supplies no normals.
+__global__ void __launch_bounds__(128) normals_kernel(NnIndex ix, int n, int k, float4 *nrm) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 q = ix.pts[s];
+    if (__float_as_int(q.w) == 0x7fffffff) {
+        nrm[s] = make_float4(NAN, NAN, NAN, 0.f);
+        return;
+    }
+    KnnList nb;
+    nb.init(k);
+    knn_search(q.x, q.y, q.z, ix, nb);
+    double mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int m = 0;
+    for (int j = 0; j < k; ++j) {
+        if (nb.pos[j] < 0) break;
+        const float4 p = __ldg(ix.pts + nb.pos[j]);
+        const double x = p.x, y = p.y, z = p.z;
+        mean[0] += x; mean[1] += y; mean[2] += z;
+        cov[0] += x * x; cov[1] += x * y; cov[2] += x * z; cov[4] += y * y; cov[5] += y * z; cov[8] += z * z;
+        ++m;
+    }
+    if (m < 3) {
+        nrm[s] = make_float4(NAN, NAN, NAN, 0.f);
+        return;
+    }
+    for (int d = 0; d < 3; ++d) mean[d] /= (double) m;
+    cov[0] = cov[0] / m - mean[0] * mean[0];
+    cov[1] = cov[1] / m - mean[0] * mean[1];
+    cov[2] = cov[2] / m - mean[0] * mean[2];
+    cov[4] = cov[4] / m - mean[1] * mean[1];
+    cov[5] = cov[5] / m - mean[1] * mean[2];
+    cov[8] = cov[8] / m - mean[2] * mean[2];
+    cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+    double U[9];
+    eig_sym3_desc(cov, U);
+    double nx = U[2], ny = U[5], nz = U[8];  // column of the smallest |eigenvalue|
+    if (nx * (double) q.x + ny * (double) q.y + nz * (double) q.z > 0) {
+        nx = -nx; ny = -ny; nz = -nz;
+    }
+    nrm[s] = make_float4((float) nx, (float) ny, (float) nz, 0.f);
+}
+
 template <class T>
 int grow(T *&ptr, size_t &cap, size_t want) {
     if (want <= cap) return WAVECU_OK;
@@ -278,6 +325,7 @@ void MortonCloud::release() {
 int TargetIndex::set_points(const float *xyzw, size_t n, bool from_device) {
     dirty = true;
     nrm_n = 0;
+    normals_estimated = false;
     return cloud.upload(xyzw, n, from_device);
 }
 
@@ -328,6 +376,26 @@ int TargetIndex::build() {
     ++cloud.launches;
     WCU_CHECK(cudaGetLastError());
     dirty = false;
+    normals_estimated = false;
+    return WAVECU_OK;
+}
+
+int TargetIndex::estimate_normals(int k) {
+    WCU_CHECK(cudaSetDevice(cloud.device));
+    const size_t n = cloud.n;
+    if (n > nrm_sorted_cap) {
+        if (d_nrm_sorted) WCU_CHECK(cudaFree(d_nrm_sorted));
+        d_nrm_sorted = nullptr;
+        WCU_CHECK(cudaMalloc((void **) &d_nrm_sorted, (n + n / 8 + 64) * sizeof(float4)));
+        nrm_sorted_cap = n + n / 8 + 64;
+    }
+    if (n) {
+        k = std::max(3, std::min(k, kMaxKnn));
+        normals_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, cloud.stream>>>(index(), (int) n, k, d_nrm_sorted);
+        ++cloud.launches;
+        WCU_CHECK(cudaGetLastError());
+    }
+    normals_estimated = true;
     return WAVECU_OK;
 }
 

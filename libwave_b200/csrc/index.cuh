@@ -75,6 +75,10 @@ struct TargetIndex {
     int set_points(const float *xyzw, size_t n, bool from_device);
     int set_normals(const float *nxyzw, size_t n, bool from_device);
     int build();             // sort + tree; clears dirty
+    // fills d_nrm_sorted with unit normals estimated from the k nearest neighbours of every target
+    // point (principal direction of least variance, oriented towards the sensor origin)
+    int estimate_normals(int k);
+    bool normals_estimated = false;
     void release();
     struct NnIndex index() const;
 };

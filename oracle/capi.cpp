@@ -307,3 +307,7 @@ void wo_gicp_align(const float *src, size_t n_src, const float *tgt, size_t n_tg
 }
 
 }  // extern "C"
+
+extern "C" void wo_estimate_normals(const float *cloud, size_t n, int k, float *normals_xyzw) {
+    estimate_normals(cloud, n, k, normals_xyzw);
+}

@@ -659,3 +659,53 @@ void gicp_align(const float *source, size_t n_src, const float *target, size_t n
 }
 
 }  // namespace wo
+
+// ---- surface normals for the point-to-plane extension --------------------------
+// Not in the reference (its ICP is point-to-point); the repo's definition, shared with the device
+// code through DESIGN.md: k nearest neighbours (the point itself included), fp64 covariance,
+// direction of least variance, flipped towards the sensor origin.
+namespace wo {
+
+void estimate_normals(const float *cloud, size_t n, int k, float *normals_xyzw) {
+    KdTree tree(cloud, n, 4);
+    std::vector<int> idx((size_t) k);
+    std::vector<float> d2((size_t) k);
+    for (size_t i = 0; i < n; ++i) {
+        float *o = normals_xyzw + 4 * i;
+        o[3] = 0.f;
+        const float *q = cloud + 4 * i;
+        if (!(std::isfinite(q[0]) && std::isfinite(q[1]) && std::isfinite(q[2]))) {
+            o[0] = o[1] = o[2] = std::numeric_limits<float>::quiet_NaN();
+            continue;
+        }
+        const int m = tree.knn(q, k, idx.data(), d2.data());
+        if (m < 3) {
+            o[0] = o[1] = o[2] = std::numeric_limits<float>::quiet_NaN();
+            continue;
+        }
+        double mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < m; ++j) {
+            const float *p = cloud + 4 * (size_t) idx[(size_t) j];
+            const double x = p[0], y = p[1], z = p[2];
+            mean[0] += x; mean[1] += y; mean[2] += z;
+            cov[0] += x * x; cov[1] += x * y; cov[2] += x * z; cov[4] += y * y; cov[5] += y * z; cov[8] += z * z;
+        }
+        for (int d = 0; d < 3; ++d) mean[d] /= (double) m;
+        cov[0] = cov[0] / m - mean[0] * mean[0];
+        cov[1] = cov[1] / m - mean[0] * mean[1];
+        cov[2] = cov[2] / m - mean[0] * mean[2];
+        cov[4] = cov[4] / m - mean[1] * mean[1];
+        cov[5] = cov[5] / m - mean[1] * mean[2];
+        cov[8] = cov[8] / m - mean[2] * mean[2];
+        cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+        double ev[3], U[9];
+        eig_sym3_desc(cov, ev, U);
+        double nx = U[2], ny = U[5], nz = U[8];
+        if (nx * (double) q[0] + ny * (double) q[1] + nz * (double) q[2] > 0) {
+            nx = -nx; ny = -ny; nz = -nz;
+        }
+        o[0] = (float) nx; o[1] = (float) ny; o[2] = (float) nz;
+    }
+}
+
+}  // namespace wo

@@ -34,4 +34,7 @@ bool gicp_covariances(const float *cloud_xyzw, size_t n, const KdTree &tree, int
 void gicp_align(const float *source, size_t n_src, const float *target, size_t n_tgt, const GicpParams &prm,
                 GicpResult &res);
 
+// k-NN PCA normals oriented towards the origin (point-to-plane extension; see gicp.cpp)
+void estimate_normals(const float *cloud_xyzw, size_t n, int k, float *normals_xyzw);
+
 }  // namespace wo

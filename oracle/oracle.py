@@ -392,3 +392,13 @@ def gicp_align(source, target, *, corr_rand=10, max_iter=100, r_eps=1e-8) -> Gic
     r.T, r.converged, r.iterations, r.n_corr = T.reshape(4, 4), bool(conv.value), iters.value, nc.value
     r.inner_iterations, r.evaluations, r.delta = inner.value, evals.value, trace[:ntr.value].copy()
     return r
+
+
+def estimate_normals(cloud, k=10):
+    """k-NN PCA normals oriented towards the origin (the repo's point-to-plane extension)."""
+    c = xyzw(cloud)
+    L = lib()
+    L.wo_estimate_normals.argtypes = [_fp, C.c_size_t, C.c_int, _fp]
+    out = np.empty_like(c)
+    L.wo_estimate_normals(_f(c), c.shape[0], k, _f(out))
+    return out

@@ -165,3 +165,37 @@ def test_information_lum_vs_lumold(W, oracle, testscan):
     m.params.covar_estimator = W.INFO_LUM
     m.estimateInfo()
     assert np.array_equal(m.getInfo(), lumold)
+
+
+def test_point_to_plane_bit_exact_and_estimated_normals(W, oracle):
+    """SURVEY.md 8(a) A7 (north-star extension; the reference has no point-to-plane estimator):
+    with supplied normals the GPU follows the oracle's PointToPlaneLLS restatement bit for bit; with
+    no normals it estimates them on the device (k-NN PCA) and must land on the oracle's result for
+    the oracle's own estimate of the same normals."""
+    from libwave_b200 import synth
+    src, tgt, nrm = synth.scan_pair(10_000, return_normals=True)
+    m = W.ICPMatcher(W.ICPMatcherParams(res=-1, estimator=W.EST_POINT_TO_PLANE))
+    m.setup(src, tgt)
+    m.setTargetNormals(nrm)
+    assert m.match()
+    ref = oracle.icp_align(src, tgt, estimator=oracle.EST_POINT_TO_PLANE, sum_mode=oracle.SUM_EXACT, target_normals=nrm)
+    mse, ncorr, Ttr = m.trace()
+    assert m.iterations == ref.iterations and np.array_equal(ncorr, ref.n_corr)
+    assert np.array_equal(mse, ref.mse)
+    assert np.abs(Ttr - ref.T_trace).max() < 1e-7      # cos/sin of the device vs glibc: <= 1 fp32 ulp
+    assert np.abs(m.getResult() - ref.T.astype(np.float64)).max() < 1e-6
+    q, mm, d2 = m.correspondences()
+    assert np.array_equal(mm, ref.corr_match)
+    pcl = oracle.icp_align(src, tgt, estimator=oracle.EST_POINT_TO_PLANE, sum_mode=oracle.SUM_PCL, target_normals=nrm)
+    assert np.abs(m.getResult()[:3, 3] - pcl.T[:3, 3]).max() < 1e-4
+    assert rot_angle(m.getResult()[:3, :3], pcl.T[:3, :3]) < 1e-5
+
+    m2 = W.ICPMatcher(W.ICPMatcherParams(res=-1, estimator=W.EST_POINT_TO_PLANE))
+    m2.setup(src, tgt)                                   # no normals given
+    assert m2.match()
+    est = oracle.estimate_normals(tgt, 10)
+    ref2 = oracle.icp_align(src, tgt, estimator=oracle.EST_POINT_TO_PLANE, sum_mode=oracle.SUM_EXACT,
+                            target_normals=est)
+    assert m2.iterations == ref2.iterations
+    assert np.abs(m2.getResult()[:3, 3] - ref2.T[:3, 3]).max() < 1e-4
+    assert rot_angle(m2.getResult()[:3, :3], ref2.T[:3, :3]) < 1e-5
