@@ -121,11 +121,19 @@ __global__ void unsort_corr_kernel(const float4 *__restrict__ cur, const int *__
 struct IcpHandle {
     wavecu_icp_params prm;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    // Three streams per handle.  `stream` (the caller's, or our own): target build, iterations, results.
+    // `aux`: the source cloud's sort, which overlaps the target build.  `copy`: every upload, so that
+    // the H2D copy of one cloud overlaps the sort / tree build of the previous one (a 1 M-point
+    // match moves 48 MB over PCIe - as long as the whole device-side build).
+    cudaStream_t stream = nullptr, aux = nullptr, copy = nullptr;
     bool own_stream = false;
+    cudaEvent_t ev_main = nullptr, ev_src_sorted = nullptr, ev_first = nullptr;
+    bool first_recorded = false, first_marked = false;
+    long long launches_mark = 0;
     MortonCloud src;
     TargetIndex tgt;
     bool src_dirty = true;
+    bool src_sorted_fresh = false;   // src.d_sorted holds an unconsumed Morton sort of the uploaded source
 
     // iteration buffers
     int *d_nn_pos = nullptr, *d_nn_idx = nullptr;
@@ -169,6 +177,12 @@ struct IcpHandle {
     std::vector<cudaEvent_t> ev_pool;
 
     int init();
+    int on_set_source(bool from_device);
+    int on_set_target(bool from_device);
+    int set_source(const float *xyzw, size_t n, bool from_device);
+    int set_target(const float *xyzw, size_t n, bool from_device);
+    int set_target_normals(const float *nxyzw, size_t n, bool from_device);
+    int mark_first();
     int ensure_iter_buffers(size_t n_src_pad, int max_iter);
     int align(double *T_out, int *converged, int *iterations, int *state);
     int stash_originals();
@@ -189,9 +203,19 @@ int IcpHandle::init() {
     src.key_bits = 10;  // the source order only has to be spatially coherent: 31 sorted bits, 4 passes
     if (const char *e = getenv("WAVECU_SRC_BITS")) src.key_bits = std::max(1, std::min(21, atoi(e)));  // tuning knob
     if (const char *e = getenv("WAVECU_TGT_BITS")) tgt.cloud.key_bits = std::max(1, std::min(21, atoi(e)));
+    WCU_CHECK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+    WCU_CHECK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    WCU_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+    WCU_CHECK(cudaEventCreateWithFlags(&ev_src_sorted, getenv("WAVECU_TIMELINE") ? cudaEventDefault
+                                                                                  : cudaEventDisableTiming));
+    WCU_CHECK(cudaEventCreate(&ev_first));
     src.device = tgt.cloud.device = device;
-    src.stream = tgt.cloud.stream = stream;
-    cudaFuncSetAttribute(correspond_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    src.stream = aux;
+    tgt.cloud.stream = stream;
+    src.copy_stream = tgt.cloud.copy_stream = copy;
+    // shared-memory carve-out left at the driver default (32 KB here): measured 5 % faster than MaxL1
+    if (const char *e = getenv("WAVECU_CARVEOUT"))  // tuning knob
+        cudaFuncSetAttribute(correspond_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
     WCU_CHECK(cudaMalloc((void **) &d_mc, sizeof(MatchConsts)));
     WCU_CHECK(cudaMalloc((void **) &d_st, sizeof(IcpState)));
     WCU_CHECK(cudaMalloc((void **) &d_acc, sizeof(Acc128) * kAccSlots * kMaxAcc));
@@ -202,6 +226,74 @@ int IcpHandle::init() {
     vox.stream = stream;
     for (int i = 0; i < kDepth; ++i) WCU_CHECK(cudaEventCreateWithFlags(&ev_ring[i], cudaEventDisableTiming));
     return WAVECU_OK;
+}
+
+int IcpHandle::mark_first() {
+    if (!first_marked) {
+        launches_mark = src.launches + tgt.cloud.launches;
+        first_marked = true;
+    }
+    if (profiling && !first_recorded) {
+        WCU_CHECK(cudaEventRecord(ev_first, stream));
+        first_recorded = true;
+    }
+    return WAVECU_OK;
+}
+
+// Uploads are asynchronous; at full resolution the source sort (aux stream) and the target build
+// (main stream) are queued right behind their copies, so they run while the next cloud is still
+// crossing PCIe.  Device-resident inputs were produced on the caller's stream: the copy waits for it.
+int IcpHandle::on_set_source(bool from_device) {
+    src_is_user = true;
+    have_orig_src = false;
+    src_dirty = true;
+    have_result = false;
+    src_sorted_fresh = false;
+    int rc = mark_first();
+    if (rc) return rc;
+    if (from_device) {  // the D2D copy and the sort run on aux: order them behind the caller's stream
+        WCU_CHECK(cudaEventRecord(ev_main, stream));
+        WCU_CHECK(cudaStreamWaitEvent(aux, ev_main, 0));
+    }
+    return WAVECU_OK;
+}
+
+int IcpHandle::on_set_target(bool from_device) {
+    tgt_is_user = true;
+    have_orig_tgt = false;
+    have_result = false;
+    (void) from_device;  // device-resident targets are copied on the main stream itself
+    return mark_first();
+}
+
+int IcpHandle::set_source(const float *xyzw, size_t n, bool from_device) {
+    WCU_CHECK(cudaSetDevice(device));
+    int rc = on_set_source(from_device);
+    if (rc) return rc;
+    rc = src.upload(xyzw, n, from_device);
+    if (rc) return rc;
+    if (!(prm.res > 0) && n) {  // full resolution: this cloud is the working cloud - sort it right away
+        rc = src.sort(n);
+        if (rc) return rc;
+        WCU_CHECK(cudaEventRecord(ev_src_sorted, aux));
+        src_sorted_fresh = true;
+    }
+    return WAVECU_OK;
+}
+
+int IcpHandle::set_target(const float *xyzw, size_t n, bool from_device) {
+    WCU_CHECK(cudaSetDevice(device));
+    int rc = on_set_target(from_device);
+    if (rc) return rc;
+    rc = tgt.set_points(xyzw, n, from_device);
+    if (rc) return rc;
+    if (!(prm.res > 0) && n) return tgt.build();  // full resolution: build the search tree behind the copy
+    return WAVECU_OK;
+}
+
+int IcpHandle::set_target_normals(const float *nxyzw, size_t n, bool from_device) {
+    WCU_CHECK(cudaSetDevice(device));
+    return tgt.set_normals(nxyzw, n, from_device);
 }
 
 int IcpHandle::ensure_iter_buffers(size_t n_src_pad, int max_iter) {
@@ -237,7 +329,8 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     const size_t n_src = src.n, n_tgt = tgt.cloud.n;
     const int max_iter = std::max(prm.max_iter, 1);
     stats = wavecu_stats{};
-    const long long launches0 = src.launches + tgt.cloud.launches;
+    const long long launches0 = first_marked ? launches_mark : src.launches + tgt.cloud.launches;
+    first_marked = false;
     cudaEvent_t e_begin = nullptr, e_built = nullptr, e_end = nullptr;
     size_t ev_used = 0;
     auto next_event = [&]() -> cudaEvent_t {
@@ -259,18 +352,33 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     const size_t n_src_pad = n_src;
     int rc = ensure_iter_buffers(std::max<size_t>(n_src_pad, 1), max_iter);
     if (rc) return rc;
+    // the working cloud is consumed by the iterations, so the source is re-sorted for every align
+    // (on the aux stream, concurrently with the target build) unless set_source already queued it
+    if (!src_sorted_fresh) {
+        WCU_CHECK(cudaEventRecord(ev_main, stream));   // load_level / restore write src.d_raw on the main stream
+        WCU_CHECK(cudaStreamWaitEvent(aux, ev_main, 0));
+        rc = src.sort(std::max<size_t>(n_src_pad, 1));
+        if (rc) return rc;
+        WCU_CHECK(cudaEventRecord(ev_src_sorted, aux));
+    }
     if (tgt.dirty) {
         rc = tgt.build();
         if (rc) return rc;
     }
-    if (prm.estimator == WAVECU_EST_POINT_TO_PLANE && tgt.nrm_n != n_tgt && !tgt.normals_estimated) {
-        // no normals from the caller: estimate them on the target's own tree (k = 10 neighbours)
-        rc = tgt.estimate_normals(10);
-        if (rc) return rc;
+    if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
+        if (tgt.nrm_n == n_tgt) {
+            if (tgt.nrm_dirty) {
+                rc = tgt.sort_normals();
+                if (rc) return rc;
+            }
+        } else if (!tgt.normals_estimated) {
+            // no normals from the caller: estimate them on the target's own tree (k = 10 neighbours)
+            rc = tgt.estimate_normals(10);
+            if (rc) return rc;
+        }
     }
-    // the working cloud is consumed by the iterations, so the source is re-sorted for every align
-    rc = src.sort(std::max<size_t>(n_src_pad, 1));
-    if (rc) return rc;
+    WCU_CHECK(cudaStreamWaitEvent(stream, ev_src_sorted, 0));
+    src_sorted_fresh = false;
     src_dirty = false;
     long long extra_launches = 0;
     if (n_src) {
@@ -356,10 +464,23 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     stats.pairs = (long long) last.iter * (long long) n_src;
     if (profiling) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, e_begin, e_built);
+        // the build may have been queued by set_source / set_target already: count from the first of them
+        cudaEvent_t e_start = first_recorded ? ev_first : e_begin;
+        cudaEventElapsedTime(&ms, e_start, e_built);
         stats.build_ms = ms;
-        cudaEventElapsedTime(&ms, e_begin, e_end);
+        cudaEventElapsedTime(&ms, e_start, e_end);
         stats.total_ms = ms;
+        if (getenv("WAVECU_TIMELINE") && first_recorded) {  // debugging aid: where the streams were, in ms
+            auto at = [&](cudaEvent_t e) {
+                float t = -1.0f;
+                if (e && cudaEventElapsedTime(&t, ev_first, e) != cudaSuccess) { cudaGetLastError(); t = -1.0f; }
+                return t;
+            };
+            fprintf(stderr, "[wavecu timeline ms] src_up %.3f tgt_up %.3f nrm_up %.3f src_sorted %.3f tgt_used %.3f "
+                            "align_begin %.3f built %.3f end %.3f\n", at(src.ev_up), at(tgt.cloud.ev_up),
+                    at(tgt.ev_nrm_up), at(ev_src_sorted), at(tgt.cloud.ev_used), at(e_begin), at(e_built), at(e_end));
+        }
+        first_recorded = false;
         // only iterations that did work count (speculative launches past `done` return at once)
         for (int k = 0; k < last.iter + (last.state == WAVECU_CONV_NO_CORRESPONDENCES ? 1 : 0) &&
                         (size_t) (3 * k + 2) < it_ev.size(); ++k) {
@@ -379,6 +500,9 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
 
 // ---- ICPMatcher::match(), src/icp.cpp:75-133 -------------------------------------------------------
 int IcpHandle::stash_originals() {
+    // the caller's clouds may still be in flight on the copy / aux streams
+    WCU_CHECK(cudaStreamSynchronize(copy));
+    WCU_CHECK(cudaStreamSynchronize(aux));
     if (src_is_user) {
         if (src.n > orig_src_cap) {
             if (d_orig_src) WCU_CHECK(cudaFree(d_orig_src));
@@ -412,6 +536,7 @@ int IcpHandle::restore_originals() {
         int rc = src.upload((const float *) d_orig_src, n_orig_src, true);
         if (rc) return rc;
         src_is_user = true;
+        src_sorted_fresh = false;
     }
     if (!tgt_is_user && have_orig_tgt) {
         int rc = tgt.set_points((const float *) d_orig_tgt, n_orig_tgt, true);
@@ -430,6 +555,7 @@ int IcpHandle::load_level(float leaf, const double *running) {
     rc = vox.filter(d_orig_src, n_orig_src, leaf, src.d_raw, &n_out, nullptr);
     if (rc) return rc;
     src.n = n_out;
+    src_sorted_fresh = false;
     if (running) {
         rc = affine3d_inplace(src.d_raw, n_out, running, stream);
         if (rc) return rc;
@@ -706,6 +832,10 @@ void IcpHandle::release() {
     for (auto &e : ev_ring)
         if (e) cudaEventDestroy(e);
     for (auto e : ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ev_main, ev_src_sorted, ev_first})
+        if (e) cudaEventDestroy(e);
+    if (aux) cudaStreamDestroy(aux);
+    if (copy) cudaStreamDestroy(copy);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -771,41 +901,27 @@ int wavecu_icp_set_params(wavecu_icp *w, const wavecu_icp_params *params) {
 
 int wavecu_icp_set_source(wavecu_icp *w, const float *xyzw, size_t n) {
     if (!w || (!xyzw && n)) return WAVECU_ERR_ARG;
-    w->h.src_is_user = true;
-    w->h.have_orig_src = false;
-    w->h.src_dirty = true;
-    w->h.have_result = false;
-    return w->h.src.upload(xyzw, n, false);
+    return w->h.set_source(xyzw, n, false);
 }
 int wavecu_icp_set_source_device(wavecu_icp *w, const void *d, size_t n) {
     if (!w || (!d && n)) return WAVECU_ERR_ARG;
-    w->h.src_is_user = true;
-    w->h.have_orig_src = false;
-    w->h.src_dirty = true;
-    w->h.have_result = false;
-    return w->h.src.upload((const float *) d, n, true);
+    return w->h.set_source((const float *) d, n, true);
 }
 int wavecu_icp_set_target(wavecu_icp *w, const float *xyzw, size_t n) {
     if (!w || (!xyzw && n)) return WAVECU_ERR_ARG;
-    w->h.tgt_is_user = true;
-    w->h.have_orig_tgt = false;
-    w->h.have_result = false;
-    return w->h.tgt.set_points(xyzw, n, false);
+    return w->h.set_target(xyzw, n, false);
 }
 int wavecu_icp_set_target_device(wavecu_icp *w, const void *d, size_t n) {
     if (!w || (!d && n)) return WAVECU_ERR_ARG;
-    w->h.tgt_is_user = true;
-    w->h.have_orig_tgt = false;
-    w->h.have_result = false;
-    return w->h.tgt.set_points((const float *) d, n, true);
+    return w->h.set_target((const float *) d, n, true);
 }
 int wavecu_icp_set_target_normals(wavecu_icp *w, const float *nxyzw, size_t n) {
     if (!w || (!nxyzw && n)) return WAVECU_ERR_ARG;
-    return w->h.tgt.set_normals(nxyzw, n, false);
+    return w->h.set_target_normals(nxyzw, n, false);
 }
 int wavecu_icp_set_target_normals_device(wavecu_icp *w, const void *d, size_t n) {
     if (!w || (!d && n)) return WAVECU_ERR_ARG;
-    return w->h.tgt.set_normals((const float *) d, n, true);
+    return w->h.set_target_normals((const float *) d, n, true);
 }
 
 int wavecu_icp_align(wavecu_icp *w, double T_out[16], int *converged, int *iterations, int *state) {

@@ -279,15 +279,33 @@ int MortonCloud::upload(const float *xyzw, size_t n_points, bool from_device) {
     int rc = reserve(n_points, 0);
     if (rc) return rc;
     n = n_points;
+    // host clouds cross PCIe on the copy stream; device-resident ones are a ~10 us D2D copy that simply
+    // goes in front of the sort on `stream` (which the caller has ordered behind the producer)
+    const bool async_copy = copy_stream && !from_device;
+    cudaStream_t cs = async_copy ? copy_stream : stream;
+    if (async_copy) {
+        if (!ev_up) {
+            const unsigned fl = getenv("WAVECU_TIMELINE") ? cudaEventDefault : cudaEventDisableTiming;
+            WCU_CHECK(cudaEventCreateWithFlags(&ev_up, fl));
+            WCU_CHECK(cudaEventCreateWithFlags(&ev_used, fl));
+        }
+        if (used_pending) WCU_CHECK(cudaStreamWaitEvent(copy_stream, ev_used, 0));
+    }
     if (n)
         WCU_CHECK(cudaMemcpyAsync(d_raw, xyzw, n * sizeof(float4),
-                                  from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+                                  from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
+    up_pending = false;
+    if (async_copy) {
+        WCU_CHECK(cudaEventRecord(ev_up, copy_stream));
+        up_pending = true;
+    }
     return WAVECU_OK;
 }
 
 int MortonCloud::sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_extra_out) {
     int rc = reserve(n, n_sorted_pad);
     if (rc) return rc;
+    if (copy_stream && up_pending) WCU_CHECK(cudaStreamWaitEvent(stream, ev_up, 0));
     bbox_init_kernel<<<1, 32, 0, stream>>>(d_bbox);
     ++launches;
     if (n) {
@@ -310,10 +328,18 @@ int MortonCloud::sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_e
         ++launches;
     }
     WCU_CHECK(cudaGetLastError());
+    if (copy_stream && ev_used) {  // the next host upload must not overwrite d_raw under this sort
+        WCU_CHECK(cudaEventRecord(ev_used, stream));
+        used_pending = true;
+    }
     return WAVECU_OK;
 }
 
 void MortonCloud::release() {
+    if (ev_up) cudaEventDestroy(ev_up);
+    if (ev_used) cudaEventDestroy(ev_used);
+    ev_up = ev_used = nullptr;
+    up_pending = used_pending = false;
     for (void *p : {(void *) d_raw, (void *) d_sorted, (void *) d_bbox, (void *) d_keys, (void *) d_keys_alt,
                     (void *) d_vals, (void *) d_vals_alt, d_tmp})
         if (p) cudaFree(p);
@@ -337,11 +363,59 @@ int TargetIndex::set_normals(const float *nxyzw, size_t n, bool from_device) {
     }
     int rc = grow(d_nrm_raw, nrm_cap, n);
     if (rc) return rc;
+    const bool async_copy = cloud.copy_stream && !from_device;
+    cudaStream_t cs = async_copy ? cloud.copy_stream : cloud.stream;
     if (n)
         WCU_CHECK(cudaMemcpyAsync(d_nrm_raw, nxyzw, n * sizeof(float4),
-                                  from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cloud.stream));
+                                  from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
+    nrm_up_pending = false;
+    if (async_copy) {
+        if (!ev_nrm_up)
+            WCU_CHECK(cudaEventCreateWithFlags(&ev_nrm_up, getenv("WAVECU_TIMELINE") ? cudaEventDefault
+                                                                                    : cudaEventDisableTiming));
+        WCU_CHECK(cudaEventRecord(ev_nrm_up, cloud.copy_stream));
+        nrm_up_pending = true;
+    }
     nrm_n = n;
-    dirty = true;
+    nrm_dirty = true;   // the tree does not depend on the normals: only their gather is redone
+    return WAVECU_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(kBuildThreads) gather_extra_kernel(const float4 *__restrict__ in,
+                                                                     const unsigned long long *__restrict__ keys,
+                                                                     const unsigned *__restrict__ vals, size_t n,
+                                                                     int bits, float4 *out) {
+    const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((keys[i] >> (3 * bits)) == 0ull) e = in[vals[i]];
+    out[i] = e;
+}
+}  // namespace
+
+int TargetIndex::sort_normals() {
+    WCU_CHECK(cudaSetDevice(cloud.device));
+    const size_t n = cloud.n;
+    if (nrm_n != n) {
+        nrm_dirty = false;
+        return WAVECU_OK;
+    }
+    if (n > nrm_sorted_cap) {
+        if (d_nrm_sorted) WCU_CHECK(cudaFree(d_nrm_sorted));
+        d_nrm_sorted = nullptr;
+        WCU_CHECK(cudaMalloc((void **) &d_nrm_sorted, (n + n / 8 + 64) * sizeof(float4)));
+        nrm_sorted_cap = n + n / 8 + 64;
+    }
+    if (cloud.copy_stream && nrm_up_pending) WCU_CHECK(cudaStreamWaitEvent(cloud.stream, ev_nrm_up, 0));
+    if (n) {
+        gather_extra_kernel<<<(unsigned) ((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, cloud.stream>>>(
+            d_nrm_raw, cloud.d_keys, cloud.d_vals, n, cloud.key_bits, d_nrm_sorted);
+        ++cloud.launches;
+        WCU_CHECK(cudaGetLastError());
+    }
+    nrm_dirty = false;
+    normals_estimated = false;
     return WAVECU_OK;
 }
 
@@ -362,14 +436,9 @@ int TargetIndex::build() {
         node_cap = a;
     }
     if (!d_root) WCU_CHECK(cudaMalloc((void **) &d_root, sizeof(TreeRoot)));
-    if (nrm_n && n > nrm_sorted_cap) {
-        if (d_nrm_sorted) WCU_CHECK(cudaFree(d_nrm_sorted));
-        d_nrm_sorted = nullptr;
-        WCU_CHECK(cudaMalloc((void **) &d_nrm_sorted, (n + n / 8 + 64) * sizeof(float4)));
-        nrm_sorted_cap = n + n / 8 + 64;
-    }
-    int rc = cloud.sort(std::max<size_t>(n, 1), nrm_n ? d_nrm_raw : nullptr, nrm_n ? d_nrm_sorted : nullptr);
+    int rc = cloud.sort(std::max<size_t>(n, 1));
     if (rc) return rc;
+    if (nrm_n) nrm_dirty = true;
     if (n) WCU_CHECK(cudaMemsetAsync(d_other, 0xff, n * sizeof(int), cloud.stream));
     lbvh_kernel<<<(unsigned) std::max<size_t>(1, (n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0,
                   cloud.stream>>>(cloud.d_keys, cloud.d_sorted, cloud.d_bbox, d_nodes, d_other, d_root);
@@ -403,6 +472,9 @@ void TargetIndex::release() {
     cloud.release();
     for (void *p : {(void *) d_nodes, (void *) d_other, (void *) d_root, (void *) d_nrm_raw, (void *) d_nrm_sorted})
         if (p) cudaFree(p);
+    if (ev_nrm_up) cudaEventDestroy(ev_nrm_up);
+    ev_nrm_up = nullptr;
+    nrm_up_pending = nrm_dirty = false;
     d_nodes = nullptr; d_other = nullptr; d_root = nullptr; d_nrm_raw = d_nrm_sorted = nullptr;
     node_cap = nrm_cap = nrm_sorted_cap = nrm_n = 0;
 }

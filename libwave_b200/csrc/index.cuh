@@ -20,7 +20,13 @@ namespace wavecu {
 
 struct MortonCloud {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // sort / gather kernels
+    // Optional second stream for upload(): the copy then overlaps kernels queued on `stream` (another
+    // cloud's sort, the tree build).  ev_up orders sort() behind the copy, ev_used orders the next
+    // copy behind the last sort that read d_raw.  nullptr: everything runs on `stream`.
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_used = nullptr;
+    bool up_pending = false, used_pending = false;
     size_t n = 0;            // points in d_raw
     size_t cap = 0;          // allocated points
     float4 *d_raw = nullptr;     // as given (original order)
@@ -74,7 +80,10 @@ struct TargetIndex {
 
     int set_points(const float *xyzw, size_t n, bool from_device);
     int set_normals(const float *nxyzw, size_t n, bool from_device);
-    int build();             // sort + tree; clears dirty
+    int build();             // sort + tree; clears dirty (normals are gathered by sort_normals())
+    int sort_normals();      // d_nrm_sorted <- d_nrm_raw in the Morton order of the last build
+    cudaEvent_t ev_nrm_up = nullptr;
+    bool nrm_up_pending = false, nrm_dirty = false;
     // fills d_nrm_sorted with unit normals estimated from the k nearest neighbours of every target
     // point (principal direction of least variance, oriented towards the sensor origin)
     int estimate_normals(int k);
@@ -162,8 +171,12 @@ struct NnIndex {
 };
 
 // Ordered top-down search of the subtree under internal node `link` (its box is already known to
-// be within the bound).  "while-while": all lanes descend until each holds a leaf (or is done),
-// then all scan their leaves together.
+// be within the bound).  "while-while" with one pop site: all lanes descend until each holds a
+// leaf, has hit a dead end (both children beyond the bound) or is done; then the lanes holding a
+// leaf scan it together, and all lanes pop their next subtree together.  (Popping inside the
+// descent on a dead end costs a divergent pass of ~2 active lanes per occurrence: -10 % kernel
+// time on the 1 M-point lidar workload, profiles/r01_nn_variants.md.)
+constexpr int kLinkPop = (int) 0x80000001;  // dead end; leaf links are >= -2^30, so no collision
 __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, const TNode *__restrict__ nodes,
                                                const float4 *__restrict__ pts, int link, float &best, int &best_idx,
                                                int &best_pos) {
@@ -186,18 +199,13 @@ __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, con
                 }
                 link = ln;
             } else {
-                link = kLinkDone;
-                while (sp > 0) {
-                    --sp;
-                    if (stack_d[sp] <= best) {
-                        link = stack_link[sp];
-                        break;
-                    }
-                }
+                link = kLinkPop;
             }
         }
-        if (link == kLinkDone) return;
-        scan_leaf(qx, qy, qz, pts, link, best, best_idx, best_pos);
+        if (link != kLinkPop) {
+            if (link == kLinkDone) return;
+            scan_leaf(qx, qy, qz, pts, link, best, best_idx, best_pos);
+        }
         link = kLinkDone;
         while (sp > 0) {
             --sp;
@@ -274,18 +282,11 @@ __device__ __forceinline__ void knn_search(float qx, float qy, float qz, const N
                 }
                 link = ln;
             } else {
-                link = kLinkDone;
-                while (sp > 0) {
-                    --sp;
-                    if (stack_d[sp] <= out.worst()) {
-                        link = stack_link[sp];
-                        break;
-                    }
-                }
+                link = kLinkPop;
             }
         }
-        if (link == kLinkDone) return;
-        {
+        if (link != kLinkPop) {
+            if (link == kLinkDone) return;
             const int start = leaf_start(link), cnt = leaf_count(link);
             for (int k = 0; k < cnt; ++k) {
                 const float4 p = __ldg(ix.pts + start + k);
