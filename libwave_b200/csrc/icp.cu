@@ -151,6 +151,8 @@ struct IcpHandle {
     // pinned host mirrors
     int *h_done = nullptr;  // ring of kDepth flags
     IcpState *h_st = nullptr;
+    TraceRow *h_trace = nullptr;  // pinned: the first kTracePrefetch trace rows
+    static constexpr int kTracePrefetch = 16;
     static constexpr int kDepth = 3;
     cudaEvent_t ev_ring[kDepth] = {nullptr, nullptr, nullptr};
 
@@ -221,6 +223,7 @@ int IcpHandle::init() {
     WCU_CHECK(cudaMalloc((void **) &d_acc, sizeof(Acc128) * kAccSlots * kMaxAcc));
     WCU_CHECK(cudaHostAlloc((void **) &h_done, sizeof(int) * kDepth, cudaHostAllocDefault));
     WCU_CHECK(cudaHostAlloc((void **) &h_st, sizeof(IcpState), cudaHostAllocDefault));
+    WCU_CHECK(cudaHostAlloc((void **) &h_trace, sizeof(TraceRow) * kTracePrefetch, cudaHostAllocDefault));
     WCU_CHECK(cudaHostAlloc((void **) &h_acc, sizeof(Acc128) * kAccSlots * kMaxAcc, cudaHostAllocDefault));
     vox.device = device;
     vox.stream = stream;
@@ -446,6 +449,10 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     if (profiling) WCU_CHECK(cudaEventRecord(e_end, stream));
     WCU_CHECK(cudaMemcpyAsync(h_st, d_st, sizeof(IcpState), cudaMemcpyDeviceToHost, stream));
     WCU_CHECK(cudaMemcpyAsync(&last_mc, d_mc, sizeof(MatchConsts), cudaMemcpyDeviceToHost, stream));
+    // most matches stop within a few iterations: their trace rows ride along with the state read-back
+    const int n_pre = std::min(launched, kTracePrefetch);
+    if (n_pre > 0)
+        WCU_CHECK(cudaMemcpyAsync(h_trace, d_trace, sizeof(TraceRow) * (size_t) n_pre, cudaMemcpyDeviceToHost, stream));
     WCU_CHECK(cudaStreamSynchronize(stream));
     WCU_CHECK(cudaGetLastError());
     last = *h_st;
@@ -454,7 +461,9 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         last.state = WAVECU_CONV_NOT_CONVERGED;
     }
     trace.resize((size_t) std::max(0, last.iter));
-    if (last.iter > 0)
+    if (last.iter > 0 && last.iter <= n_pre)
+        std::memcpy(trace.data(), h_trace, sizeof(TraceRow) * (size_t) last.iter);
+    else if (last.iter > 0)
         WCU_CHECK(cudaMemcpy(trace.data(), d_trace, sizeof(TraceRow) * (size_t) last.iter, cudaMemcpyDeviceToHost));
     have_result = true;
     result_n_src = n_src;
@@ -829,6 +838,7 @@ void IcpHandle::release() {
     if (h_acc) cudaFreeHost(h_acc);
     if (h_done) cudaFreeHost(h_done);
     if (h_st) cudaFreeHost(h_st);
+    if (h_trace) cudaFreeHost(h_trace);
     for (auto &e : ev_ring)
         if (e) cudaEventDestroy(e);
     for (auto e : ev_pool) cudaEventDestroy(e);

@@ -302,12 +302,57 @@ int MortonCloud::upload(const float *xyzw, size_t n_points, bool from_device) {
     return WAVECU_OK;
 }
 
-int MortonCloud::sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_extra_out) {
-    int rc = reserve(n, n_sorted_pad);
-    if (rc) return rc;
-    if (copy_stream && up_pending) WCU_CHECK(cudaStreamWaitEvent(stream, ev_up, 0));
+bool graphs_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("WAVECU_NO_GRAPH");
+        return !(e && *e && *e != '0');
+    }();
+    return on;
+}
+
+namespace {
+// Replays `cache` if its key still matches, otherwise captures `enqueue` (thread-local capture: other
+// host threads keep using CUDA) and instantiates it.  `counter` is the owner's launch statistic.
+template <class F>
+int run_captured(GraphCache &cache, cudaStream_t stream, const unsigned long long (&key)[8], long long &counter,
+                 F &&enqueue) {
+    if (!graphs_enabled()) return enqueue();
+    if (!cache.matches(key)) {
+        cache.release();
+        const long long before = counter;
+        WCU_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+        const long long per_replay = counter - before;
+        counter = before;
+        if (rc != WAVECU_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc != WAVECU_OK) return rc;
+            return enqueue();  // not capturable here: plain launches
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&cache.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            cache.exec = nullptr;
+            cudaGetLastError();
+            return enqueue();
+        }
+        for (int i = 0; i < 8; ++i) cache.key[i] = key[i];
+        cache.launches = per_replay;
+    }
+    WCU_CHECK(cudaGraphLaunch(cache.exec, stream));
+    counter += cache.launches;
+    return WAVECU_OK;
+}
+}  // namespace
+
+int MortonCloud::enqueue_sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_extra_out) {
     bbox_init_kernel<<<1, 32, 0, stream>>>(d_bbox);
     ++launches;
+    d_keys_sorted = d_keys;
+    d_vals_sorted = d_vals;
     if (n) {
         const int grid = (int) std::min<size_t>((n + kBuildThreads - 1) / kBuildThreads, 148 * 4);
         bbox_kernel<<<grid, kBuildThreads, 0, stream>>>(d_raw, n, d_bbox);
@@ -319,15 +364,26 @@ int MortonCloud::sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_e
         size_t need = tmp_bytes;
         WCU_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, need, kb, vb, (int) n, 0, 3 * key_bits + 1, stream));
         launches += 2 + (3 * key_bits + 8) / 8;  // histogram + scan + onesweep passes (CUB-internal)
-        if (kb.Current() != d_keys) std::swap(d_keys, d_keys_alt);
-        if (vb.Current() != d_vals) std::swap(d_vals, d_vals_alt);
+        d_keys_sorted = kb.Current();
+        d_vals_sorted = vb.Current();
     }
     if (n_sorted_pad) {
         gather_kernel<<<(unsigned) ((n_sorted_pad + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, stream>>>(
-            d_raw, d_keys, d_vals, n, n_sorted_pad, key_bits, d_sorted, d_extra_in, d_extra_out);
+            d_raw, d_keys_sorted, d_vals_sorted, n, n_sorted_pad, key_bits, d_sorted, d_extra_in, d_extra_out);
         ++launches;
     }
     WCU_CHECK(cudaGetLastError());
+    return WAVECU_OK;
+}
+
+int MortonCloud::pre_sort(size_t n_sorted_pad) {
+    int rc = reserve(n, n_sorted_pad);
+    if (rc) return rc;
+    if (copy_stream && up_pending) WCU_CHECK(cudaStreamWaitEvent(stream, ev_up, 0));
+    return WAVECU_OK;
+}
+
+int MortonCloud::post_sort() {
     if (copy_stream && ev_used) {  // the next host upload must not overwrite d_raw under this sort
         WCU_CHECK(cudaEventRecord(ev_used, stream));
         used_pending = true;
@@ -335,7 +391,21 @@ int MortonCloud::sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_e
     return WAVECU_OK;
 }
 
+int MortonCloud::sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_extra_out) {
+    int rc = pre_sort(n_sorted_pad);
+    if (rc) return rc;
+    const unsigned long long key[8] = {(unsigned long long) n, (unsigned long long) n_sorted_pad,
+                                       (unsigned long long) (uintptr_t) d_raw, (unsigned long long) (uintptr_t) d_sorted,
+                                       (unsigned long long) (uintptr_t) d_keys, (unsigned long long) (uintptr_t) d_extra_in,
+                                       (unsigned long long) (uintptr_t) d_extra_out, (unsigned long long) key_bits};
+    rc = run_captured(sort_graph, stream, key, launches,
+                      [&] { return enqueue_sort(n_sorted_pad, d_extra_in, d_extra_out); });
+    if (rc) return rc;
+    return post_sort();
+}
+
 void MortonCloud::release() {
+    sort_graph.release();
     if (ev_up) cudaEventDestroy(ev_up);
     if (ev_used) cudaEventDestroy(ev_used);
     ev_up = ev_used = nullptr;
@@ -344,6 +414,7 @@ void MortonCloud::release() {
                     (void *) d_vals, (void *) d_vals_alt, d_tmp})
         if (p) cudaFree(p);
     d_raw = d_sorted = nullptr; d_bbox = nullptr; d_keys = d_keys_alt = nullptr; d_vals = d_vals_alt = nullptr;
+    d_keys_sorted = nullptr; d_vals_sorted = nullptr;
     d_tmp = nullptr;
     cap = sorted_cap = tmp_bytes = n = 0;
 }
@@ -410,7 +481,7 @@ int TargetIndex::sort_normals() {
     if (cloud.copy_stream && nrm_up_pending) WCU_CHECK(cudaStreamWaitEvent(cloud.stream, ev_nrm_up, 0));
     if (n) {
         gather_extra_kernel<<<(unsigned) ((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, cloud.stream>>>(
-            d_nrm_raw, cloud.d_keys, cloud.d_vals, n, cloud.key_bits, d_nrm_sorted);
+            d_nrm_raw, cloud.d_keys_sorted, cloud.d_vals_sorted, n, cloud.key_bits, d_nrm_sorted);
         ++cloud.launches;
         WCU_CHECK(cudaGetLastError());
     }
@@ -436,16 +507,33 @@ int TargetIndex::build() {
         node_cap = a;
     }
     if (!d_root) WCU_CHECK(cudaMalloc((void **) &d_root, sizeof(TreeRoot)));
-    int rc = cloud.sort(std::max<size_t>(n, 1));
+    int rc = cloud.pre_sort(std::max<size_t>(n, 1));
+    if (rc) return rc;
+    const unsigned long long key[8] = {(unsigned long long) n, (unsigned long long) (uintptr_t) cloud.d_raw,
+                                       (unsigned long long) (uintptr_t) cloud.d_sorted,
+                                       (unsigned long long) (uintptr_t) cloud.d_keys,
+                                       (unsigned long long) (uintptr_t) d_nodes, (unsigned long long) (uintptr_t) d_other,
+                                       (unsigned long long) (uintptr_t) d_root, (unsigned long long) cloud.key_bits};
+    rc = run_captured(build_graph, cloud.stream, key, cloud.launches, [&] { return enqueue_build(); });
+    if (rc) return rc;
+    rc = cloud.post_sort();
     if (rc) return rc;
     if (nrm_n) nrm_dirty = true;
-    if (n) WCU_CHECK(cudaMemsetAsync(d_other, 0xff, n * sizeof(int), cloud.stream));
-    lbvh_kernel<<<(unsigned) std::max<size_t>(1, (n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0,
-                  cloud.stream>>>(cloud.d_keys, cloud.d_sorted, cloud.d_bbox, d_nodes, d_other, d_root);
-    ++cloud.launches;
-    WCU_CHECK(cudaGetLastError());
     dirty = false;
     normals_estimated = false;
+    return WAVECU_OK;
+}
+
+// Morton sort + one-launch radix-tree construction, as one capturable launch sequence
+int TargetIndex::enqueue_build() {
+    const size_t n = cloud.n;
+    int rc = cloud.enqueue_sort(std::max<size_t>(n, 1), nullptr, nullptr);
+    if (rc) return rc;
+    if (n) WCU_CHECK(cudaMemsetAsync(d_other, 0xff, n * sizeof(int), cloud.stream));
+    lbvh_kernel<<<(unsigned) std::max<size_t>(1, (n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0,
+                  cloud.stream>>>(cloud.d_keys_sorted, cloud.d_sorted, cloud.d_bbox, d_nodes, d_other, d_root);
+    ++cloud.launches;
+    WCU_CHECK(cudaGetLastError());
     return WAVECU_OK;
 }
 
@@ -469,6 +557,7 @@ int TargetIndex::estimate_normals(int k) {
 }
 
 void TargetIndex::release() {
+    build_graph.release();
     cloud.release();
     for (void *p : {(void *) d_nodes, (void *) d_other, (void *) d_root, (void *) d_nrm_raw, (void *) d_nrm_sorted})
         if (p) cudaFree(p);

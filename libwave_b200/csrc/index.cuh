@@ -18,6 +18,26 @@
 
 namespace wavecu {
 
+// A captured launch sequence, replayed while its key (sizes and buffer addresses) stays the same:
+// the build of one cloud is ~25 short kernels, and enqueueing them one by one costs the host more
+// time (~0.1 ms) than a small cloud's build takes on the device.
+struct GraphCache {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long launches = 0;
+    bool matches(const unsigned long long (&k)[8]) const {
+        if (!exec) return false;
+        for (int i = 0; i < 8; ++i)
+            if (key[i] != k[i]) return false;
+        return true;
+    }
+    void release() {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+    }
+};
+bool graphs_enabled();  // false with WAVECU_NO_GRAPH=1 (debugging / profiling aid)
+
 struct MortonCloud {
     int device = 0;
     cudaStream_t stream = nullptr;        // sort / gather kernels
@@ -32,8 +52,11 @@ struct MortonCloud {
     float4 *d_raw = nullptr;     // as given (original order)
     float4 *d_sorted = nullptr;  // Morton order, w = original index bits
     unsigned *d_bbox = nullptr;  // 6 order-preserving uints: lo xyz, hi xyz
-    unsigned long long *d_keys = nullptr, *d_keys_alt = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys_alt = nullptr;   // unsorted keys / radix-sort double buffer
     unsigned *d_vals = nullptr, *d_vals_alt = nullptr;
+    unsigned long long *d_keys_sorted = nullptr;   // whichever of the two buffers the sort left its result in
+    unsigned *d_vals_sorted = nullptr;
+    GraphCache sort_graph;
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
     size_t sorted_cap = 0;
@@ -44,6 +67,10 @@ struct MortonCloud {
     int upload(const float *xyzw, size_t n_points, bool from_device);
     // bbox + Morton keys + radix sort + gather into d_sorted[0..n_sorted_pad) (pads = +inf)
     int sort(size_t n_sorted_pad, const float4 *d_extra_in = nullptr, float4 *d_extra_out = nullptr);
+    // the bare launch sequence of sort() on `stream` (buffers reserved by the caller; capturable)
+    int enqueue_sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_extra_out);
+    int pre_sort(size_t n_sorted_pad);   // reserve + order behind the pending upload
+    int post_sort();                     // mark d_raw as consumed
     void release();
 };
 
@@ -81,6 +108,8 @@ struct TargetIndex {
     int set_points(const float *xyzw, size_t n, bool from_device);
     int set_normals(const float *nxyzw, size_t n, bool from_device);
     int build();             // sort + tree; clears dirty (normals are gathered by sort_normals())
+    int enqueue_build();
+    GraphCache build_graph;
     int sort_normals();      // d_nrm_sorted <- d_nrm_raw in the Morton order of the last build
     cudaEvent_t ev_nrm_up = nullptr;
     bool nrm_up_pending = false, nrm_dirty = false;
@@ -180,8 +209,7 @@ constexpr int kLinkPop = (int) 0x80000001;  // dead end; leaf links are >= -2^30
 __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, const TNode *__restrict__ nodes,
                                                const float4 *__restrict__ pts, int link, float &best, int &best_idx,
                                                int &best_pos) {
-    int stack_link[kStackDepth];
-    float stack_d[kStackDepth];
+    float2 stack[kStackDepth];  // (box bound, link bits): one 8-byte local load per pop
     int sp = 0;
     for (;;) {
         while (link >= 0) {
@@ -190,14 +218,10 @@ __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, con
             const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
             const bool right_first = d1 < d0;
             const float dn = right_first ? d1 : d0, df = right_first ? d0 : d1;
-            const int ln = __float_as_int(right_first ? c.w : a.w), lf = __float_as_int(right_first ? a.w : c.w);
+            const float ln = right_first ? c.w : a.w, lf = right_first ? a.w : c.w;
             if (dn <= best) {
-                if (df <= best) {
-                    stack_link[sp] = lf;
-                    stack_d[sp] = df;
-                    ++sp;
-                }
-                link = ln;
+                if (df <= best) stack[sp++] = make_float2(df, lf);
+                link = __float_as_int(ln);
             } else {
                 link = kLinkPop;
             }
@@ -208,9 +232,9 @@ __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, con
         }
         link = kLinkDone;
         while (sp > 0) {
-            --sp;
-            if (stack_d[sp] <= best) {
-                link = stack_link[sp];
+            const float2 e = stack[--sp];
+            if (e.x <= best) {
+                link = __float_as_int(e.y);
                 break;
             }
         }
