@@ -22,7 +22,13 @@ void set_last_error(const std::string &msg);
         }                                                                                            \
     } while (0)
 
-constexpr int kLeaf = 8;                // a leaf is a run of <= 8 consecutive Morton-sorted points
+// A leaf of the target tree is a run of <= kLeaf consecutive Morton-sorted points.  kLeaf = 1: every
+// leaf is one point, stored in its parent's record as a degenerate box, so the 1-NN walk is one
+// uniform loop of node steps (no separate leaf-scan phase for the lanes of a warp to wait on).
+#ifndef WCU_LEAF
+#define WCU_LEAF 1
+#endif
+constexpr int kLeaf = WCU_LEAF;
 constexpr int kAccSlots = 16;           // accumulator replicas (atomic contention spreading)
 constexpr int kMaxAcc = 40;             // values per slot (p2p uses 17, point-to-plane 33)
 

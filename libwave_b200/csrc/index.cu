@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
     const float4 p = pts[i];
     float lox = p.x, loy = p.y, loz = p.z, hix = p.x, hiy = p.y, hiz = p.z;
     int link = make_leaf_link(i, 1);
+    float tag = p.w;  // a single-point child carries the point's original index in hi.w
     for (;;) {
         if (l == 0 && r == n - 1) {
             root->lo = make_float4(lox, loy, loz, __int_as_float(link));
@@ -146,10 +147,10 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
         TNode *nd = nodes + par;
         if (parent_right) {
             nd->lo0 = make_float4(lox, loy, loz, __int_as_float(link));
-            nd->hi0 = make_float4(hix, hiy, hiz, 0.0f);
+            nd->hi0 = make_float4(hix, hiy, hiz, tag);
         } else {
             nd->lo1 = make_float4(lox, loy, loz, __int_as_float(link));
-            nd->hi1 = make_float4(hix, hiy, hiz, 0.0f);
+            nd->hi1 = make_float4(hix, hiy, hiz, tag);
         }
         __threadfence();
         const int prev = atomicExch(&other[par], parent_right ? l : r);
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
         lox = fminf(lox, slo.x); loy = fminf(loy, slo.y); loz = fminf(loz, slo.z);
         hix = fmaxf(hix, shi.x); hiy = fmaxf(hiy, shi.y); hiz = fmaxf(hiz, shi.z);
         link = (r - l + 1 <= kLeaf) ? make_leaf_link(l, r - l + 1) : par;
+        tag = 0.0f;
     }
 }
 

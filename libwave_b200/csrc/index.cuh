@@ -77,6 +77,8 @@ struct MortonCloud {
 // Traversal node of the radix-tree LBVH: both children's boxes and links in one aligned 64-byte
 // record, so one node visit is one segment load.  link >= 0: index of the child's own node;
 // link < 0: the child is a leaf, a run of <= kLeaf consecutive sorted points (make_leaf_link).
+// A single-point child is the degenerate box lo = hi = the point, with the point's original index
+// in hi.w: aabb_dist of such a box is bit-for-bit l2_simple of the point.
 // Halves are addressed as 2*node + side.
 struct __align__(64) TNode {
     float4 lo0;  // xyz, w = link0 (int bits)
@@ -206,6 +208,64 @@ struct NnIndex {
 // descent on a dead end costs a divergent pass of ~2 active lanes per occurrence: -10 % kernel
 // time on the 1 M-point lidar workload, profiles/r01_nn_variants.md.)
 constexpr int kLinkPop = (int) 0x80000001;  // dead end; leaf links are >= -2^30, so no collision
+#if WCU_LEAF == 1
+// Single-point leaves: one uniform loop.  A node step measures both children; a point child is
+// consumed on the spot (its "box" distance is its exact distance), a subtree child within the bound
+// is entered (the nearer one first, the other pushed).  A lane whose step leaves it without a
+// subtree pops one stack entry per round; a stale entry (bound tightened since the push) just costs
+// that lane one idle round.  Every lane of a warp therefore runs the same few instructions per
+// round, whatever mix of descending, point testing and popping the lanes are in.
+__device__ __forceinline__ void subtree_search(float qx, float qy, float qz, const TNode *__restrict__ nodes,
+                                               const float4 *__restrict__ pts, int link, float &best, int &best_idx,
+                                               int &best_pos) {
+    (void) pts;
+    // (box bound, link bits) entries; the newest one lives in registers, so a pop needs no load on
+    // its critical path (the entry below it is fetched from local memory for the *next* pop).  The
+    // bottom of the stack is a sentinel that no bound admits.
+    float2 stack[kStackDepth];
+    float2 top = make_float2(INFINITY, __int_as_float(kLinkDone));
+    int sp = 0;
+    // distances are >= 0, so (distance bits, original index) compares as one unsigned 64-bit key:
+    // "closer, or as close with a lower index"
+    unsigned long long best_key = ((unsigned long long) __float_as_uint(best) << 32) | (unsigned) best_idx;
+    for (;;) {
+        if (link >= 0) {
+            const float4 a = __ldg(&nodes[link].lo0), b = __ldg(&nodes[link].hi0);
+            const float4 c = __ldg(&nodes[link].lo1), d = __ldg(&nodes[link].hi1);
+            const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
+            const int l0 = __float_as_int(a.w), l1 = __float_as_int(c.w);
+            const unsigned long long k0 = ((unsigned long long) __float_as_uint(d0) << 32) | __float_as_uint(b.w);
+            const unsigned long long k1 = ((unsigned long long) __float_as_uint(d1) << 32) | __float_as_uint(d.w);
+            if (l0 < 0 && k0 < best_key) {
+                best_key = k0;
+                best_pos = ~l0;
+            }
+            if (l1 < 0 && k1 < best_key) {
+                best_key = k1;
+                best_pos = ~l1;
+            }
+            const float bound = __uint_as_float((unsigned) (best_key >> 32));
+            const bool in0 = l0 >= 0 && d0 <= bound, in1 = l1 >= 0 && d1 <= bound;
+            if (in0 && in1) {
+                const bool right_first = d1 < d0;
+                stack[sp++] = top;
+                top = right_first ? make_float2(d0, a.w) : make_float2(d1, c.w);
+                link = right_first ? l1 : l0;
+            } else {
+                link = in0 ? l0 : (in1 ? l1 : kLinkPop);
+            }
+        }
+        if (link < 0) {
+            const int tl = __float_as_int(top.y);
+            if (tl == kLinkDone) break;
+            link = (top.x <= __uint_as_float((unsigned) (best_key >> 32))) ? tl : kLinkPop;
+            top = stack[--sp];
+        }
+    }
+    best = __uint_as_float((unsigned) (best_key >> 32));
+    best_idx = (int) (unsigned) best_key;
+}
+#else
 __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, const TNode *__restrict__ nodes,
                                                const float4 *__restrict__ pts, int link, float &best, int &best_idx,
                                                int &best_pos) {
@@ -240,6 +300,8 @@ __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, con
         }
     }
 }
+
+#endif
 
 inline NnIndex TargetIndex::index() const {
     NnIndex ix;
