@@ -63,12 +63,13 @@ int main(int argc, char **argv) {
     size_t nq = Q[0].size(); std::vector<uint32_t> qperm(nq); std::iota(qperm.begin(), qperm.end(), 0);
     { std::vector<uint64_t> qk(nq); for (size_t i = 0; i < nq; ++i) qk[i] = mkey(&Q[0][i].x, 10); std::stable_sort(qperm.begin(), qperm.end(), [&](uint32_t a, uint32_t b) { return qk[a] < qk[b]; }); }
     const float THR = 9.f;
-    for (int variant = (argc > 0 && getenv("V0")) ? atoi(getenv("V0")) : 0; variant < 13; ++variant) {
+    for (int variant = (argc > 0 && getenv("V0")) ? atoi(getenv("V0")) : 0; variant < (getenv("PG") ? atoi(getenv("V0")) + 1 : 13); ++variant) {
         int G = 0, FMAX = 0; bool lbinit = false; int levelsync = 0; float alpha = 0.f;
         switch (variant) { case 0: break; case 1: lbinit = true; break; case 2: G = 32; FMAX = 8; lbinit = true; break; case 3: G = 32; FMAX = 16; lbinit = true; break;
             case 4: G = 128; FMAX = 16; lbinit = true; break; case 5: G = 128; FMAX = 32; lbinit = true; break; case 6: G = 32; FMAX = 32; lbinit = true; break;
             case 7: G = 32; FMAX = 8; levelsync = 1; break; case 8: G = 32; FMAX = 16; levelsync = 1; break; case 9: G = 32; FMAX = 32; levelsync = 1; break;
             case 10: G = 32; FMAX = 16; levelsync = 1; alpha = 0.5f; break; case 11: G = 32; FMAX = 32; levelsync = 1; alpha = 0.5f; break; case 12: G = 32; FMAX = 32; levelsync = 1; alpha = 1.0f; break; }
+        if (getenv("PG")) { G = atoi(getenv("PG")); FMAX = atoi(getenv("PF")); levelsync = 1; lbinit = true; alpha = 0.f; }
         printf("variant %d: group %d fmax %d lower-bound-init %d\n", variant, G, FMAX, (int) lbinit);
         std::vector<int> warm(nq, -1);
         for (int k = 0; k < K; ++k) {
