@@ -149,12 +149,11 @@ struct IcpHandle {
     int trace_cap = 0;
 
     // pinned host mirrors
-    int *h_done = nullptr;  // ring of kDepth flags
+    int *h_progress = nullptr;  // mapped: (launch number << 1) | done, written by the solve kernel
     IcpState *h_st = nullptr;
     TraceRow *h_trace = nullptr;  // pinned: the first kTracePrefetch trace rows
     static constexpr int kTracePrefetch = 16;
     static constexpr int kDepth = 3;
-    cudaEvent_t ev_ring[kDepth] = {nullptr, nullptr, nullptr};
 
     // results of the last align
     bool have_result = false;
@@ -221,13 +220,12 @@ int IcpHandle::init() {
     WCU_CHECK(cudaMalloc((void **) &d_mc, sizeof(MatchConsts)));
     WCU_CHECK(cudaMalloc((void **) &d_st, sizeof(IcpState)));
     WCU_CHECK(cudaMalloc((void **) &d_acc, sizeof(Acc128) * kAccSlots * kMaxAcc));
-    WCU_CHECK(cudaHostAlloc((void **) &h_done, sizeof(int) * kDepth, cudaHostAllocDefault));
+    WCU_CHECK(cudaHostAlloc((void **) &h_progress, sizeof(int), cudaHostAllocMapped));
     WCU_CHECK(cudaHostAlloc((void **) &h_st, sizeof(IcpState), cudaHostAllocDefault));
     WCU_CHECK(cudaHostAlloc((void **) &h_trace, sizeof(TraceRow) * kTracePrefetch, cudaHostAllocDefault));
     WCU_CHECK(cudaHostAlloc((void **) &h_acc, sizeof(Acc128) * kAccSlots * kMaxAcc, cudaHostAllocDefault));
     vox.device = device;
     vox.stream = stream;
-    for (int i = 0; i < kDepth; ++i) WCU_CHECK(cudaEventCreateWithFlags(&ev_ring[i], cudaEventDisableTiming));
     return WAVECU_OK;
 }
 
@@ -407,7 +405,10 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     ia.st = d_st;
     ia.mc = d_mc;
     ia.acc = d_acc;
-    SolveArgs so{d_st, d_mc, d_acc, d_trace, max_iter, prm.t_eps, prm.fit_eps};
+    int *d_progress = nullptr;
+    WCU_CHECK(cudaHostGetDevicePointer((void **) &d_progress, h_progress, 0));
+    *(volatile int *) h_progress = 0;
+    SolveArgs so{d_st, d_mc, d_acc, d_trace, max_iter, prm.t_eps, prm.fit_eps, d_progress, 0};
     const unsigned grid_nn = (unsigned) std::max<size_t>(1, (n_src + kIterThreads - 1) / kIterThreads);
     const unsigned grid_red = (unsigned) std::max<size_t>(
         1, (n_src + kReduceThreads * kReducePerThread - 1) / (kReduceThreads * kReducePerThread));
@@ -424,6 +425,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             it_ev.push_back(next_event());
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
         }
+        so.launch = k + 1;
         if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
             reduce_kernel<WAVECU_EST_POINT_TO_PLANE><<<grid_red, kReduceThreads, 0, stream>>>(ia);
             solve_kernel<WAVECU_EST_POINT_TO_PLANE><<<1, 64, 0, stream>>>(so);
@@ -436,14 +438,26 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
         }
         ++launched;
-        const int slot = k % kDepth;
-        WCU_CHECK(cudaMemcpyAsync(&h_done[slot], &d_st->done, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        WCU_CHECK(cudaEventRecord(ev_ring[slot], stream));
-        // look at the flag of iteration k-(kDepth-1): the device always has work queued behind it
+        // follow the device kDepth-1 iterations behind (it always has work queued): the solve kernel of
+        // launch j publishes (j << 1) | done in mapped host memory
         if (k >= kDepth - 1) {
-            const int old = (k - (kDepth - 1)) % kDepth;
-            WCU_CHECK(cudaEventSynchronize(ev_ring[old]));
-            if (h_done[old]) finished = true;
+            const int need = k - (kDepth - 1) + 1;
+            int v, spins = 0;
+            while (((v = *(volatile int *) h_progress) >> 1) < need) {
+                if (++spins % 4096 == 0) {
+                    const cudaError_t q = cudaStreamQuery(stream);
+                    if (q != cudaErrorNotReady) {  // finished (or failed) without publishing: stop waiting
+                        if (q != cudaSuccess) WCU_CHECK(q);
+                        v = *(volatile int *) h_progress;
+                        if ((v >> 1) < need) v |= 1;
+                        break;
+                    }
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            if (v & 1) finished = true;
         }
     }
     if (profiling) WCU_CHECK(cudaEventRecord(e_end, stream));
@@ -836,11 +850,9 @@ void IcpHandle::release() {
     for (void *p : {(void *) d_orig_src, (void *) d_orig_tgt, (void *) d_pos2})
         if (p) cudaFree(p);
     if (h_acc) cudaFreeHost(h_acc);
-    if (h_done) cudaFreeHost(h_done);
+    if (h_progress) cudaFreeHost(h_progress);
     if (h_st) cudaFreeHost(h_st);
     if (h_trace) cudaFreeHost(h_trace);
-    for (auto &e : ev_ring)
-        if (e) cudaEventDestroy(e);
     for (auto e : ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : {ev_main, ev_src_sorted, ev_first})
         if (e) cudaEventDestroy(e);

@@ -24,8 +24,14 @@ namespace wavecu {
 #define WCU_ITER_THREADS 128
 #endif
 constexpr int kIterThreads = WCU_ITER_THREADS;  // correspondence kernel: one query per thread
-constexpr int kReduceThreads = 256;     // reduction kernel
-constexpr int kReducePerThread = 8;
+#ifndef WCU_RED_THREADS
+#define WCU_RED_THREADS 256
+#endif
+#ifndef WCU_RED_PER
+#define WCU_RED_PER 8
+#endif
+constexpr int kReduceThreads = WCU_RED_THREADS;     // reduction kernel
+constexpr int kReducePerThread = WCU_RED_PER;
 constexpr int kReduceWarps = kReduceThreads / 32;
 
 struct IterArgs {
@@ -216,7 +222,16 @@ struct SolveArgs {
     TraceRow *trace;
     int max_iter;
     double t_eps, fit_eps;
+    // mapped host word, (launch number << 1) | done: lets the host follow the iterations without
+    // putting a copy or an event between the kernels
+    volatile int *progress;
+    int launch;
 };
+
+__device__ __forceinline__ void publish_progress(const SolveArgs &a, int done) {
+    *a.progress = (a.launch << 1) | (done ? 1 : 0);
+    __threadfence_system();
+}
 
 // Rotation maximising trace(R^T S): one-sided Jacobi on S, fixed pair order, <= 12 sweeps (stops
 // early only at an exact fixed point, which leaves the result unchanged).
@@ -328,7 +343,10 @@ __device__ inline bool solve6(const double A_in[36], const double b_in[6], doubl
 template <int EST>
 __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
     constexpr int NV = EstTraits<EST>::NV;
-    if (a.st->done) return;
+    if (a.st->done) {
+        if (threadIdx.x == 0) publish_progress(a, 1);
+        return;
+    }
     // threads 0..NV: one accumulator each, summed over the slots (and cleared for the next
     // iteration); then thread 0 runs the estimator
     __shared__ unsigned long long s_lo[NV + 1];
@@ -356,6 +374,7 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
         st.converged = 0;
         st.state = WAVECU_CONV_NO_CORRESPONDENCES;
         st.done = 1;
+        publish_progress(a, 1);
         return;
     }
     const double dn = (double) n;
@@ -397,6 +416,7 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
             st.converged = 0;
             st.state = WAVECU_CONV_NO_CORRESPONDENCES;
             st.done = 1;
+            publish_progress(a, 1);
             return;
         }
         const double al = x[0], be = x[1], ga = x[2];
@@ -465,6 +485,7 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
         st.state = state;
         st.done = 1;
     }
+    publish_progress(a, conv);
 }
 
 }  // namespace wavecu
