@@ -159,6 +159,10 @@ struct IcpHandle {
     bool have_result = false;
     size_t result_n_src = 0;
     IcpState last;
+    double result[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};  // Matcher::result of the last match
+    double *d_censi = nullptr;      // per-block partial sums of the Censi estimator
+    double *h_censi = nullptr;
+    int censi_blocks = 0;
     std::vector<TraceRow> trace;
 
     // voxel-filtered / multiscale path: the clouds as the caller gave them
@@ -191,6 +195,7 @@ struct IcpHandle {
     int load_level(float leaf, const double *running);
     int match(double *T_out, int *converged, int *iterations);
     int info(int method, double *info_out);
+    int info_censi(double *info_out);
     int read_acc(int n_values, __int128 *out);
     void release();
 };
@@ -513,6 +518,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             stats.solve_ms += ms;
         }
     }
+    for (int i = 0; i < 16; ++i) result[i] = (double) last.T_final[i];
     if (T_out)
         for (int i = 0; i < 16; ++i) T_out[i] = (double) last.T_final[i];
     if (converged) *converged = last.converged;
@@ -646,6 +652,7 @@ int IcpHandle::match(double *T_out, int *converged, int *iterations) {
         rc = align(T, &conv, &total_iters, nullptr);
         if (rc) return rc;
     }
+    std::memcpy(result, T, sizeof T);  // Matcher::result of the multiscale / voxel branch
     if (T_out) std::memcpy(T_out, T, sizeof T);
     if (converged) *converged = conv;
     if (iterations) *iterations = total_iters;
@@ -715,11 +722,7 @@ int IcpHandle::info(int method, double *info_out) {
         set_last_error("estimateInfo needs a match() result");
         return WAVECU_ERR_STATE;
     }
-    if (method == WAVECU_INFO_CENSI) {
-        set_last_error("the Censi estimator is not built yet (its result is always overwritten by LUMold in the "
-                       "reference's estimateInfo fall-through, src/icp.cpp:135-142)");
-        return WAVECU_ERR_STATE;
-    }
+    if (method == WAVECU_INFO_CENSI) return info_censi(info_out);
     // estimateLUM only acts if icp.hasConverged() (icp_pcl_functions.cpp:190): otherwise keep the
     // caller's matrix untouched - signalled by returning the identity the base class starts from
     const size_t ns = result_n_src;
@@ -839,7 +842,150 @@ int IcpHandle::info(int method, double *info_out) {
     return WAVECU_OK;
 }
 
+namespace {
+
+// Eigen 3.3 MatrixBase::eulerAngles(0, 1, 2): X-Y-Z factorisation, first angle folded into [0, pi]
+void euler_angles_012(const double *R, double *out) {
+    auto at = [&](int r, int c) { return R[3 * r + c]; };
+    double r0 = std::atan2(at(1, 2), at(2, 2)), r1;
+    const double c2 = std::sqrt(at(0, 0) * at(0, 0) + at(0, 1) * at(0, 1));
+    if (r0 > 0.0) {
+        r0 -= M_PI;
+        r1 = std::atan2(-at(0, 2), -c2);
+    } else {
+        r1 = std::atan2(-at(0, 2), c2);
+    }
+    const double s1 = std::sin(r0), c1 = std::cos(r0);
+    const double r2 = std::atan2(s1 * at(2, 0) - c1 * at(1, 0), c1 * at(1, 1) - s1 * at(2, 1));
+    out[0] = -r0;
+    out[1] = -r1;
+    out[2] = -r2;
+}
+
+void mat3_mul(const double *A, const double *B, double *C) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
+}
+
+bool inverse6_host(const double *A, double *inv) {
+    for (int c = 0; c < 6; ++c) {
+        double e[6], x[6];
+        for (int i = 0; i < 6; ++i) e[i] = (i == c) ? 1.0 : 0.0;
+        if (!solve6_host(A, e, x)) return false;
+        for (int i = 0; i < 6; ++i) inv[6 * i + c] = x[i];
+    }
+    return true;
+}
+
+void mat6_mul(const double *A, const double *B, double *C) {
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 6; ++k) s += A[6 * i + k] * B[6 * k + j];
+            C[6 * i + j] = s;
+        }
+}
+
+}  // namespace
+
+// ICPMatcher::estimateCensi (src/icp.cpp:167-397): only acts if the match converged; evaluated at
+// Matcher::result over the clouds and correspondences of the last align().
+int IcpHandle::info_censi(double *info_out) {
+    for (int i = 0; i < 36; ++i) info_out[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    if (!last.converged) return WAVECU_OK;
+    const size_t ns = result_n_src;
+    if (ns == 0) {
+        for (int i = 0; i < 36; ++i) info_out[i] = std::nan("");
+        return WAVECU_OK;
+    }
+    CensiArgs ca;
+    CensiConsts &k = ca.c;
+    {
+        double L[9], Rp[9], eul[3];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) L[3 * r + c] = result[4 * r + c];
+        rotation_from_sigma(L, Rp);  // Eigen Transform::rotation(): the polar factor of the linear part
+        euler_angles_012(Rp, eul);
+        const double cr = std::cos(eul[0]), sr = std::sin(eul[0]), cp = std::cos(eul[1]), sp = std::sin(eul[1]),
+                     cy = std::cos(eul[2]), sy = std::sin(eul[2]);
+        // value, first and second derivative of each elementary rotation; R = Rz Ry Rx
+        const double X[3][9] = {{1, 0, 0, 0, cr, -sr, 0, sr, cr}, {0, 0, 0, 0, -sr, -cr, 0, cr, -sr}, {0, 0, 0, 0, -cr, sr, 0, -sr, -cr}};
+        const double Y[3][9] = {{cp, 0, sp, 0, 1, 0, -sp, 0, cp}, {-sp, 0, cp, 0, 0, 0, -cp, 0, -sp}, {-cp, 0, -sp, 0, 0, 0, sp, 0, -cp}};
+        const double Z[3][9] = {{cy, -sy, 0, sy, cy, 0, 0, 0, 1}, {-sy, -cy, 0, cy, -sy, 0, 0, 0, 0}, {-cy, sy, 0, -sy, -cy, 0, 0, 0, 0}};
+        auto prod = [&](int dz, int dy, int dx, double *out) {
+            double t[9];
+            mat3_mul(Z[dz], Y[dy], t);
+            mat3_mul(t, X[dx], out);
+        };
+        prod(0, 0, 0, k.R);
+        prod(0, 0, 1, k.dR[0]);
+        prod(0, 1, 0, k.dR[1]);
+        prod(1, 0, 0, k.dR[2]);
+        prod(0, 0, 2, k.ddR[0]);
+        prod(0, 1, 1, k.ddR[1]);
+        prod(1, 0, 1, k.ddR[2]);
+        prod(0, 2, 0, k.ddR[3]);
+        prod(1, 1, 0, k.ddR[4]);
+        prod(2, 0, 0, k.ddR[5]);
+        k.t[0] = result[3];
+        k.t[1] = result[7];
+        k.t[2] = result[11];
+        k.lin = prm.lidar_lin_covar;
+        k.ang = prm.lidar_ang_covar;
+    }
+    const int blocks = (int) std::min<size_t>((ns + kCensiThreads - 1) / kCensiThreads, (size_t) 2 * 148);
+    if (blocks > censi_blocks) {
+        if (d_censi) WCU_CHECK(cudaFree(d_censi));
+        if (h_censi) WCU_CHECK(cudaFreeHost(h_censi));
+        d_censi = h_censi = nullptr;
+        WCU_CHECK(cudaMalloc((void **) &d_censi, sizeof(double) * kCensiValues * (size_t) blocks));
+        WCU_CHECK(cudaHostAlloc((void **) &h_censi, sizeof(double) * kCensiValues * (size_t) blocks, cudaHostAllocDefault));
+        censi_blocks = blocks;
+    }
+    ca.cur = src.d_sorted;
+    ca.raw = src.d_raw;
+    ca.n_src = (int) ns;
+    ca.tgt = tgt.cloud.d_sorted;
+    ca.pos = d_nn_pos;
+    ca.partial = d_censi;
+    censi_kernel<<<blocks, kCensiThreads, 0, stream>>>(ca);
+    WCU_CHECK(cudaGetLastError());
+    WCU_CHECK(cudaMemcpyAsync(h_censi, d_censi, sizeof(double) * kCensiValues * (size_t) blocks, cudaMemcpyDeviceToHost, stream));
+    WCU_CHECK(cudaStreamSynchronize(stream));
+    double v[kCensiValues];
+    for (int i = 0; i < kCensiValues; ++i) {
+        double s = 0.0;
+        for (int b = 0; b < blocks; ++b) s += h_censi[(size_t) b * kCensiValues + i];
+        v[i] = s;
+    }
+    double H[36], M[36];
+    for (int i = 0; i < 36; ++i) H[i] = M[i] = 0.0;
+    int u = 0;
+    for (int i = 0; i < 3; ++i) {
+        H[6 * i + i] = 2.0 * v[36];
+        for (int q = 0; q < 3; ++q) H[6 * i + 3 + q] = v[u++];
+    }
+    for (int q = 0; q < 3; ++q)
+        for (int l = q; l < 3; ++l) H[6 * (3 + q) + 3 + l] = v[u++];
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) M[6 * i + j] = M[6 * j + i] = v[u++];
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < r; ++c) H[6 * r + c] = H[6 * c + r];
+    double Hi[36], A[36], B[36];
+    if (!inverse6_host(H, Hi)) {
+        for (int i = 0; i < 36; ++i) info_out[i] = std::nan("");
+        return WAVECU_OK;
+    }
+    mat6_mul(Hi, M, A);
+    mat6_mul(A, Hi, B);
+    if (!inverse6_host(B, info_out))
+        for (int i = 0; i < 36; ++i) info_out[i] = std::nan("");
+    return WAVECU_OK;
+}
+
 void IcpHandle::release() {
+    if (d_censi) cudaFree(d_censi);
+    if (h_censi) cudaFreeHost(h_censi);
     cudaSetDevice(device);
     src.release();
     tgt.release();

@@ -235,7 +235,7 @@ __device__ __forceinline__ void publish_progress(const SolveArgs &a, int done) {
 
 // Rotation maximising trace(R^T S): one-sided Jacobi on S, fixed pair order, <= 12 sweeps (stops
 // early only at an exact fixed point, which leaves the result unchanged).
-__device__ inline void rotation_from_sigma(const double S[9], double R[9]) {
+__host__ __device__ inline void rotation_from_sigma(const double S[9], double R[9]) {
     double A[3][3], V[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)

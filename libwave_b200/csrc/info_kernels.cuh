@@ -154,4 +154,142 @@ __global__ void zero_acc_kernel(Acc128 *acc) {
     }
 }
 
+// ---- Censi / Haralick closed-form covariance (ICPMatcher::estimateCensi, src/icp.cpp:167-397) ----
+// Per correspondence (a = matched target point, b = reference point as handed to the last align())
+// the second derivatives of J = | t + R a - b |^2, R = Rz(yaw) Ry(pitch) Rx(roll), at the match
+// result: d2J/dX2 (15 non-constant upper entries) and D cov_Z D^T with D = d2J/dZdX (21 entries of
+// a symmetric 6x6).  R and its first / second partial derivatives are per-match constants built on
+// the host; the measurement covariance of each point follows the reference: fp32 range, bearing
+// and elevation (sqrtf / atan2f / atanf), j diag(lin, ang, ang) j^T with the reference's j.
+// Sums are fp64 per thread -> warp -> block, one partial row per block, added by the host in
+// block order (deterministic; agreement with the CPU oracle is to ~1e-6 relative, limited by the
+// ulp-level differences between the device's and glibc's atan2f / atanf).
+constexpr int kCensiValues = 37;  // 15 of H, 21 of middle, pair count
+constexpr int kCensiThreads = 128;
+
+struct CensiConsts {
+    double t[3];
+    double R[9];
+    double dR[3][9];     // d/droll, d/dpitch, d/dyaw
+    double ddR[6][9];    // rr, rp, ry, pp, py, yy
+    double lin, ang;
+};
+
+struct CensiArgs {
+    const float4 *cur;   // Morton-ordered working source (w = original index)
+    const float4 *raw;   // the source cloud of the last align(), original order
+    int n_src;
+    const float4 *tgt;   // Morton-ordered target
+    const int *pos;      // per sorted source point: matched target position or -1
+    double *partial;     // [gridDim.x][kCensiValues]
+    CensiConsts c;
+};
+
+__device__ __forceinline__ void censi_point_cov(float x, float y, float z, double lin, double ang, double cov[9]) {
+    const float rho2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+    const double rg = (double) sqrtf(__fadd_rn(rho2, __fmul_rn(z, z)));
+    const double br = (double) atan2f(y, x);
+    const double az = (double) atanf(__fdiv_rn(z, sqrtf(rho2)));
+    const double cb = cos(br), sb = sin(br), ca = cos(az), sa = sin(az);
+    const double j[9] = {cb * sa, -rg * sb * sa, rg * cb * ca, sb * sa, rg * cb * sa, rg * ca * sb, ca, 0.0, -rg * sa};
+    const double w[3] = {lin, ang, ang};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            cov[3 * r + c] = (j[3 * r] * w[0] * j[3 * c] + j[3 * r + 1] * w[1] * j[3 * c + 1]) + j[3 * r + 2] * w[2] * j[3 * c + 2];
+}
+
+__global__ void __launch_bounds__(kCensiThreads) censi_kernel(CensiArgs a) {
+    double v[kCensiValues];
+#pragma unroll
+    for (int i = 0; i < kCensiValues; ++i) v[i] = 0.0;
+    const CensiConsts &k = a.c;
+    for (int s = blockIdx.x * kCensiThreads + threadIdx.x; s < a.n_src; s += gridDim.x * kCensiThreads) {
+        const int pos = a.pos[s];
+        if (pos < 0) continue;
+        const float4 pa = __ldg(a.tgt + pos);
+        const float4 pb = a.raw[__float_as_int(a.cur[s].w)];
+        const double av[3] = {pa.x, pa.y, pa.z}, bv[3] = {pb.x, pb.y, pb.z};
+        double e[3], g[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            e[i] = k.t[i] + ((k.R[3 * i] * av[0] + k.R[3 * i + 1] * av[1]) + k.R[3 * i + 2] * av[2]) - bv[i];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                g[q][i] = (k.dR[q][3 * i] * av[0] + k.dR[q][3 * i + 1] * av[1]) + k.dR[q][3 * i + 2] * av[2];
+        // H(t_i, k) -> v[3 i + k]; H(k, l), k <= l -> v[9 + ...]
+        int u = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) v[u++] += 2.0 * g[q][i];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int l = q; l < 3; ++l) {
+                const int sec = (q == 0) ? l : (q == 1 ? 2 + l : 5);  // rr rp ry | pp py | yy
+                const double *S = k.ddR[sec];
+                double ea = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) ea += e[i] * ((S[3 * i] * av[0] + S[3 * i + 1] * av[1]) + S[3 * i + 2] * av[2]);
+                v[u++] += 2.0 * ((g[q][0] * g[l][0] + g[q][1] * g[l][1]) + g[q][2] * g[l][2]) + 2.0 * ea;
+            }
+        // D(z, x) = d2J / dZ_z dX_x
+        double D[36];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                D[6 * i + j] = 2.0 * k.R[3 * j + i];
+                D[6 * (3 + i) + j] = (i == j) ? -2.0 : 0.0;
+            }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double rg = (k.R[i] * g[q][0] + k.R[3 + i] * g[q][1]) + k.R[6 + i] * g[q][2];
+                const double er = (e[0] * k.dR[q][i] + e[1] * k.dR[q][3 + i]) + e[2] * k.dR[q][6 + i];
+                D[6 * i + 3 + q] = 2.0 * rg + 2.0 * er;
+                D[6 * (3 + i) + 3 + q] = -2.0 * g[q][i];
+            }
+        double ca[9], cb[9];
+        censi_point_cov(pa.x, pa.y, pa.z, k.lin, k.ang, ca);
+        censi_point_cov(pb.x, pb.y, pb.z, k.lin, k.ang, cb);
+        // middle += D cov_Z D^T (cov_Z = blockdiag(ca, cb) meets D's second index), upper triangle
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double Da[3], Db[3];  // row i of D times the two covariance blocks
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                Da[l] = (D[6 * i] * ca[l] + D[6 * i + 1] * ca[3 + l]) + D[6 * i + 2] * ca[6 + l];
+                Db[l] = (D[6 * i + 3] * cb[l] + D[6 * i + 4] * cb[3 + l]) + D[6 * i + 5] * cb[6 + l];
+            }
+#pragma unroll
+            for (int j = i; j < 6; ++j)
+                v[u++] += ((Da[0] * D[6 * j] + Da[1] * D[6 * j + 1]) + Da[2] * D[6 * j + 2]) +
+                          ((Db[0] * D[6 * j + 3] + Db[1] * D[6 * j + 4]) + Db[2] * D[6 * j + 5]);
+        }
+        v[36] += 1.0;
+    }
+    __shared__ double s_part[kCensiThreads / 32][kCensiValues];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kCensiValues; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s_part[warp][i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < kCensiValues) {
+        double x = 0.0;
+#pragma unroll
+        for (int w = 0; w < kCensiThreads / 32; ++w) x += s_part[w][threadIdx.x];
+        a.partial[(size_t) blockIdx.x * kCensiValues + threadIdx.x] = x;
+    }
+}
+
 }  // namespace wavecu

@@ -165,7 +165,8 @@ class ICPMatcher(Matcher):
         return T.reshape(4, 4).copy(), bool(conv.value), iters.value, capi.CONV_STATES[state.value]
 
     def info(self, method: int):
-        """One estimator on its own: INFO_LUM (estimateLUM) or INFO_LUMOLD (estimateLUMold)."""
+        """One estimator on its own: INFO_LUM (estimateLUM), INFO_CENSI (estimateCensi) or INFO_LUMOLD
+        (estimateLUMold)."""
         info = np.empty(36, dtype=np.float64)
         capi.check(self._L.wavecu_icp_info(self._h, method, _d(info)))
         return info.reshape(6, 6).copy()

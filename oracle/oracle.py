@@ -303,6 +303,21 @@ def estimate_lum_old(aligned, target, max_corr, sum_mode=SUM_EXACT, k_quad: int 
     return info.reshape(6, 6), bool(ok)
 
 
+def estimate_censi(ref, target, corr_q, corr_m, T, lin_covar=2.5e-4, ang_covar=7.78e-9):
+    """ICPMatcher::estimateCensi (oracle/censi.cpp).  Returns (information, d2J_dX2, middle, ok)."""
+    r, t = xyzw(ref), xyzw(target)
+    q = np.ascontiguousarray(corr_q, dtype=np.int32)
+    m = np.ascontiguousarray(corr_m, dtype=np.int32)
+    T16 = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(16))
+    H, M, info = (np.empty(36, dtype=np.float64) for _ in range(3))
+    L = lib()
+    L.wo_estimate_censi.argtypes = [_fp, _fp, _ip, _ip, C.c_size_t, _dp, C.c_double, C.c_double, _dp, _dp, _dp]
+    L.wo_estimate_censi.restype = C.c_int
+    ok = L.wo_estimate_censi(_f(r), _f(t), _i(q), _i(m), q.shape[0], _d(T16), lin_covar, ang_covar, _d(H), _d(M),
+                             _d(info))
+    return info.reshape(6, 6), H.reshape(6, 6), M.reshape(6, 6), bool(ok)
+
+
 # ---- NDT (oracle/ndt.cpp) -------------------------------------------------------------------------
 class NdtParamsC(C.Structure):
     _fields_ = [("step_size", C.c_int), ("max_iter", C.c_int), ("t_eps", C.c_double), ("res", C.c_float)]

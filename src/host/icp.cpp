@@ -130,7 +130,7 @@ void ICPMatcher::estimateInfo() {
     // estimateCensi, then estimateLUMold; CENSI runs the last two; LUMold only itself.  Whatever
     // the setting, `information` therefore ends as estimateLUMold's result - that observable
     // outcome is what is produced here (estimateLUM first, so its early-return identity is
-    // overwritten exactly as in the reference; Censi's intermediate matrix is never visible).
+    // overwritten exactly as in the reference).
     double info[36];
     auto store = [&] {
         for (int r = 0; r < 6; ++r)
@@ -142,6 +142,8 @@ void ICPMatcher::estimateInfo() {
             store();
             // fall through
         case ICPMatcherParams::covar_method::CENSI:
+            // estimateCensi's matrix (wavecu_icp_info(WAVECU_INFO_CENSI)) would be overwritten by the
+            // next case before anyone can read it, so it is not computed here
         case ICPMatcherParams::covar_method::LUMold:
             if (wavecu_icp_info(this->handle, WAVECU_INFO_LUMOLD, info) != WAVECU_OK) fail("wavecu_icp_info(LUMold)");
             store();

@@ -167,6 +167,43 @@ def test_information_lum_vs_lumold(W, oracle, testscan):
     assert np.array_equal(m.getInfo(), lumold)
 
 
+@pytest.mark.parametrize("mode", ["fullres", "voxel", "multiscale"])
+def test_information_censi_vs_oracle(W, oracle, testscan, mode):
+    """estimateCensi (src/icp.cpp:167-397) over the correspondences, clouds and result of the last
+    match, in the three branches of match().  fp64 sums in a different order and the device's
+    atan2f / atanf (an ulp off glibc's now and then) bound the agreement, hence 1e-6 relative."""
+    T = np.eye(4)
+    T[:3, :3] = rot_z(np.deg2rad(-1.5)) @ rot_x(np.deg2rad(-0.8))     # negative roll: folded Euler angles
+    T[:3, 3] = (0.2, -0.1, 0.05)
+    tgt = pcl_transform(testscan, T)
+    kw = {"fullres": dict(res=-1), "voxel": dict(res=0.1, multiscale_steps=0),
+          "multiscale": dict(res=0.1, multiscale_steps=2)}[mode]
+    m = W.ICPMatcher(W.ICPMatcherParams(covar_estimator=W.INFO_CENSI, **kw))
+    m.setup(testscan, tgt)
+    assert m.match()
+    got = m.info(W.INFO_CENSI)
+    if mode == "fullres":
+        ref_cloud, tgt_cloud = testscan, tgt
+        q, mm, _ = m.correspondences()
+    else:
+        ref = oracle.icp_match(testscan, tgt, nn_threads=8, **kw)
+        ref_cloud, tgt_cloud, q, mm = ref.ds_ref, ref.ds_tgt, ref.last.corr_query, ref.last.corr_match
+        gq, gm, _ = m.correspondences()
+        assert np.array_equal(gq, q) and np.array_equal(gm, mm)
+    want, H, M, ok = oracle.estimate_censi(ref_cloud, tgt_cloud, q, mm, m.getResult())
+    assert ok and np.all(np.isfinite(got))
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    assert want[0, 0] > 0
+
+
+def rot_x(a):
+    return np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+
+
+def rot_z(a):
+    return np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+
+
 def test_point_to_plane_bit_exact_and_estimated_normals(W, oracle):
     """SURVEY.md 8(a) A7 (north-star extension; the reference has no point-to-plane estimator):
     with supplied normals the GPU follows the oracle's PointToPlaneLLS restatement bit for bit; with
