@@ -32,10 +32,11 @@ def gather_records(local: dict[int, np.ndarray], n_scans: int, device=None):
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     per = (n_scans + world - 1) // world
-    buf = torch.full((per, RECORD + 1), -1.0, dtype=torch.float64, device=device)
+    host = np.full((per, RECORD + 1), -1.0, dtype=np.float64)
     for slot, k in enumerate(shard_scan_ids(n_scans, rank, world)):
-        buf[slot, 0] = float(k)
-        buf[slot, 1:] = torch.from_numpy(local[k]).to(buf.device)
+        host[slot, 0] = float(k)
+        host[slot, 1:] = local[k]
+    buf = torch.from_numpy(host).to(device) if device is not None else torch.from_numpy(host)  # one copy
     if world > 1:
         parts = [torch.empty_like(buf) for _ in range(world)]
         dist.all_gather(parts, buf)

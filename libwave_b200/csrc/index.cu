@@ -2,6 +2,7 @@
 // The sort is cub::DeviceRadixSort (CUDA toolkit library, build step only - it runs once per
 // align() target, not per iteration); everything else is hand-written.
 #include <cub/device/device_radix_sort.cuh>
+#include <cuda/atomic>
 
 #include "../../include/wavecu.h"
 #include "index.cuh"
@@ -13,6 +14,9 @@ namespace wavecu {
 namespace {
 
 constexpr int kBuildThreads = 256;
+#ifndef WCU_LBVH_FENCE
+#define WCU_LBVH_FENCE 0
+#endif
 
 __global__ void bbox_init_kernel(unsigned *bbox) {
     if (threadIdx.x < 3) bbox[threadIdx.x] = 0xff800000u;  // lo = ordered(+inf)
@@ -152,8 +156,15 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
             nd->lo1 = make_float4(lox, loy, loz, __int_as_float(link));
             nd->hi1 = make_float4(hix, hiy, hiz, tag);
         }
+#if WCU_LBVH_FENCE
         __threadfence();
         const int prev = atomicExch(&other[par], parent_right ? l : r);
+#else
+        // release our half of the record, acquire the sibling's: one acq_rel exchange instead of a
+        // sequentially consistent fence + relaxed exchange on every level of the climb
+        const int prev = cuda::atomic_ref<int, cuda::thread_scope_device>(other[par]).exchange(
+            parent_right ? l : r, cuda::memory_order_acq_rel);
+#endif
         if (prev == -1) return;
         float4 slo, shi;
         if (parent_right) {
