@@ -206,7 +206,14 @@ int IcpHandle::init() {
         WCU_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         own_stream = true;
     }
-    src.key_bits = 10;  // the source order only has to be spatially coherent: 31 sorted bits, 4 passes
+    // the source order only has to make the queries of a warp neighbours: 12 bits per axis (37 sorted
+    // bits, 5 passes on the aux stream, off the critical path) measured 4 % faster searches than 10
+    src.key_bits = 12;
+    // target: 13 bits (extent / 8192 cells, 5 radix passes) measured best for ~1 M-point lidar targets -
+    // finer keys do not improve the tree (12: +2 % search time, 14-17: equal) and cost another sort pass
+    // (profiles/r01_nn_variants.md).  GICP keeps 15: its fp64 cost sums run in Morton order, and its
+    // iteration-for-iteration agreement with the oracle was established with that order.
+    tgt.cloud.key_bits = 13;
     if (const char *e = getenv("WAVECU_SRC_BITS")) src.key_bits = std::max(1, std::min(21, atoi(e)));  // tuning knob
     if (const char *e = getenv("WAVECU_TGT_BITS")) tgt.cloud.key_bits = std::max(1, std::min(21, atoi(e)));
     WCU_CHECK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
@@ -415,8 +422,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     *(volatile int *) h_progress = 0;
     SolveArgs so{d_st, d_mc, d_acc, d_trace, max_iter, prm.t_eps, prm.fit_eps, d_progress, 0};
     const unsigned grid_nn = (unsigned) std::max<size_t>(1, (n_src + kIterThreads - 1) / kIterThreads);
-    const unsigned grid_red = (unsigned) std::max<size_t>(
-        1, (n_src + kReduceThreads * kReducePerThread - 1) / (kReduceThreads * kReducePerThread));
+    const unsigned grid_red = (unsigned) std::max<size_t>(1, (n_src + kReduceThreads - 1) / kReduceThreads);
     std::vector<cudaEvent_t> it_ev;
     int launched = 0;
     bool finished = (n_src == 0 || n_tgt == 0);  // initCompute fails -> converged_ = false

@@ -126,91 +126,90 @@ __global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) correspond_kernel
 
 // Estimator reduction over the correspondences (A.4 / 8(a) A7): a streaming pass - 16 B working
 // point + 4 B match position + 4 B distance per source point, 16 B (+16 B normal) gathered per
-// pair - into exact 128-bit fixed-point sums.
+// pair - into exact 128-bit fixed-point sums.  One pair per thread; the 16 / 28 terms of a pair
+// are formed and warp-reduced eight at a time, so a thread never holds more than eight 64-bit
+// partial sums (48 registers instead of 104: the pass is latency bound and needs the occupancy).
+// Warp totals go to shared memory, block totals to a few 64-bit global atomics.
+__device__ __forceinline__ long long fix_term(double v, double scale) { return __double2ll_rn(v * scale); }
+
 template <int EST>
 __global__ void __launch_bounds__(kReduceThreads) reduce_kernel(IterArgs a) {
     constexpr int NV = EstTraits<EST>::NV;
     if (a.st->done) return;
-    __shared__ long long s_part[kReduceWarps][NV + 1];
+    __shared__ unsigned long long s_acc[NV + 1];
+    if (threadIdx.x <= NV) s_acc[threadIdx.x] = 0ull;
+    __syncthreads();
     const double s_lin = a.mc->s_lin, s_quad = a.mc->s_quad, s_d2 = a.mc->s_d2, s_plane = a.mc->s_plane;
-
-    long long v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = 0;
-    int count = 0;
-
-    const int base = blockIdx.x * (kReduceThreads * kReducePerThread) + threadIdx.x;
-#pragma unroll 2
-    for (int r = 0; r < kReducePerThread; ++r) {
-        const int s = base + r * kReduceThreads;
-        if (s >= a.n_src) break;
-        const int pos = a.nn_pos[s];
-        if (pos < 0) continue;
+    const int s = blockIdx.x * kReduceThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int pos = (s < a.n_src) ? a.nn_pos[s] : -1;
+    const bool pair = pos >= 0;
+    double in[7] = {0, 0, 0, 0, 0, 0, 0};  // SVD: p, q.  PLANE: J[0..5], d
+    double d2 = 0.0;
+    bool plane_ok = false;
+    if (pair) {
         const float4 c = a.cur[s];
-        const float best = a.nn_d2[s];
-        const float x = c.x, y = c.y, z = c.z;
-        ++count;
+        d2 = (double) a.nn_d2[s];
         const float4 q = __ldg(a.tgt + pos);
         if (EST == WAVECU_EST_SVD) {
-            const double px = x, py = y, pz = z, qx = q.x, qy = q.y, qz = q.z;
-            v[0] += __double2ll_rn(px * s_lin);
-            v[1] += __double2ll_rn(py * s_lin);
-            v[2] += __double2ll_rn(pz * s_lin);
-            v[3] += __double2ll_rn(qx * s_lin);
-            v[4] += __double2ll_rn(qy * s_lin);
-            v[5] += __double2ll_rn(qz * s_lin);
-            v[6] += __double2ll_rn((qx * px) * s_quad);
-            v[7] += __double2ll_rn((qx * py) * s_quad);
-            v[8] += __double2ll_rn((qx * pz) * s_quad);
-            v[9] += __double2ll_rn((qy * px) * s_quad);
-            v[10] += __double2ll_rn((qy * py) * s_quad);
-            v[11] += __double2ll_rn((qy * pz) * s_quad);
-            v[12] += __double2ll_rn((qz * px) * s_quad);
-            v[13] += __double2ll_rn((qz * py) * s_quad);
-            v[14] += __double2ll_rn((qz * pz) * s_quad);
-            v[15] += __double2ll_rn((double) best * s_d2);
+            in[0] = c.x; in[1] = c.y; in[2] = c.z;
+            in[3] = q.x; in[4] = q.y; in[5] = q.z;
         } else {
-            v[27] += __double2ll_rn((double) best * s_d2);
             const float4 nn = __ldg(a.nrm + pos);
-            if (finite3(nn.x, nn.y, nn.z)) {
+            plane_ok = finite3(nn.x, nn.y, nn.z);
+            if (plane_ok) {
                 // TransformationEstimationPointToPlaneLLS: a, b, c, d evaluated in fp32
-                double J[6];
-                J[0] = __fsub_rn(__fmul_rn(nn.z, y), __fmul_rn(nn.y, z));
-                J[1] = __fsub_rn(__fmul_rn(nn.x, z), __fmul_rn(nn.z, x));
-                J[2] = __fsub_rn(__fmul_rn(nn.y, x), __fmul_rn(nn.x, y));
-                J[3] = nn.x;
-                J[4] = nn.y;
-                J[5] = nn.z;
+                const float x = c.x, y = c.y, z = c.z;
+                in[0] = __fsub_rn(__fmul_rn(nn.z, y), __fmul_rn(nn.y, z));
+                in[1] = __fsub_rn(__fmul_rn(nn.x, z), __fmul_rn(nn.z, x));
+                in[2] = __fsub_rn(__fmul_rn(nn.y, x), __fmul_rn(nn.x, y));
+                in[3] = nn.x;
+                in[4] = nn.y;
+                in[5] = nn.z;
                 float df = __fadd_rn(__fadd_rn(__fmul_rn(nn.x, q.x), __fmul_rn(nn.y, q.y)), __fmul_rn(nn.z, q.z));
                 df = __fsub_rn(df, __fmul_rn(nn.x, x));
                 df = __fsub_rn(df, __fmul_rn(nn.y, y));
                 df = __fsub_rn(df, __fmul_rn(nn.z, z));
-                const double d = df;
-                int u = 0;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-#pragma unroll
-                    for (int j = i; j < 6; ++j) v[u++] += __double2ll_rn((J[i] * J[j]) * s_plane);
-                    v[21 + i] += __double2ll_rn((J[i] * d) * s_plane);
-                }
+                in[6] = df;
             }
         }
     }
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    warp_reduce_transpose<NV>(v, lane);
-    count = __reduce_add_sync(0xffffffffu, count);
-    constexpr int kLanesPerValue = 32 / NV;
-    if ((lane % kLanesPerValue) == 0) s_part[warp][lane / kLanesPerValue] = v[0];
-    if (lane == 0) s_part[warp][NV] = count;
+    // term t of the pair: SVD 0-2 p, 3-5 q, 6-14 q p^T (row major), 15 d2;
+    // PLANE 0-20 J^T J (upper triangle, row major), 21-26 J^T d, 27 d2, 28-31 unused
+    auto term = [&](int t) -> long long {
+        if (EST == WAVECU_EST_SVD) {
+            if (!pair) return 0;
+            if (t < 6) return fix_term(in[t], s_lin);
+            if (t < 15) return fix_term(in[3 + (t - 6) / 3] * in[(t - 6) % 3], s_quad);
+            return fix_term(d2, s_d2);
+        } else {
+            if (t == 27) return pair ? fix_term(d2, s_d2) : 0;
+            if (!plane_ok || t > 27) return 0;
+            if (t >= 21) return fix_term(in[t - 21] * in[6], s_plane);
+            int i = 0, base = 0;  // row i of the upper triangle starts at base
+            while (t >= base + (6 - i)) {
+                base += 6 - i;
+                ++i;
+            }
+            return fix_term(in[i] * in[i + (t - base)], s_plane);
+        }
+    };
+#pragma unroll
+    for (int chunk = 0; chunk < NV / 8; ++chunk) {
+        long long v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = term(chunk * 8 + k);  // indices are compile-time after unrolling
+        warp_reduce_transpose<8>(v, lane);  // lane L now holds the warp total of term chunk*8 + L/4
+        if ((lane & 3) == 0 && v[0] != 0) atomicAdd(&s_acc[chunk * 8 + (lane >> 2)], (unsigned long long) v[0]);
+    }
+    const int count = __reduce_add_sync(0xffffffffu, pair ? 1 : 0);
+    if (lane == 0 && count) atomicAdd(&s_acc[NV], (unsigned long long) count);
     __syncthreads();
     if (threadIdx.x <= NV) {
-        __int128 tot = 0;
-#pragma unroll
-        for (int w = 0; w < kReduceWarps; ++w) tot += (__int128) s_part[w][threadIdx.x];
+        const long long tot = (long long) s_acc[threadIdx.x];
         if (tot != 0) {
             Acc128 *dst = a.acc + (blockIdx.x % kAccSlots) * kMaxAcc + threadIdx.x;
-            atomic_add128(dst, (unsigned long long) tot, (long long) (tot >> 64));
+            atomic_add128(dst, (unsigned long long) tot, tot < 0 ? -1LL : 0LL);
         }
     }
 }

@@ -217,27 +217,45 @@ __global__ void __launch_bounds__(kNdtThreads) ndt_derivative_kernel(const float
         const int i1 = (int) __fsub_rn(floorf(__fmul_rn(ty, c.grid.inv)), (float) c.grid.min_b[1]);
         const int i2 = (int) __fsub_rn(floorf(__fmul_rn(tz, c.grid.inv)), (float) c.grid.min_b[2]);
         const double x[3] = {p.x, p.y, p.z};
+        // Phase 1: the 27 hash probes, independent of each other so that their loads overlap (the
+        // heavy per-hit arithmetic below would otherwise sit between them at 8 warps per SM).
+        // A centroid within `res` of the point can only live in these 27 voxels; on lidar maps
+        // 0-4 of them hold a cell.
+        int hits[27];
+        int n_hits = 0;
+        {
+            int first_key[27], vox_id[27];
+            unsigned first_h[27];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) {
+                const int v0 = i0 + (k % 3) - 1, v1 = i1 + ((k / 3) % 3) - 1, v2 = i2 + (k / 9) - 1;
+                const bool inside = !(v0 < 0 || v1 < 0 || v2 < 0 || v0 >= c.grid.div_b[0] || v1 >= c.grid.div_b[1] ||
+                                      v2 >= c.grid.div_b[2]);
+                vox_id[k] = inside ? v0 * c.grid.mul[0] + v1 * c.grid.mul[1] + v2 * c.grid.mul[2] : -2;
+                first_h[k] = hash_voxel(vox_id[k], mask);
+                first_key[k] = inside ? __ldg(table_key + first_h[k]) : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < 27; ++k) {
+                if (vox_id[k] < 0) continue;
+                unsigned h = first_h[k];
+                int key = first_key[k], slot = -1;
+                for (;;) {  // linear probing; almost always decided by the first key
+                    if (key == vox_id[k]) {
+                        slot = __ldg(table_slot + h);
+                        break;
+                    }
+                    if (key == -1) break;
+                    h = (h + 1) & mask;
+                    key = __ldg(table_key + h);
+                }
+                if (slot >= 0) hits[n_hits++] = slot;
+            }
+        }
         bool have_point_terms = false;
         double J[3][6], Hp[9][3];  // Hp: a b c d e f (eq. 6.21) -> rows 0..5, padded
-        for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int v0 = i0 + dx, v1 = i1 + dy, v2 = i2 + dz;
-                    if (v0 < 0 || v1 < 0 || v2 < 0 || v0 >= c.grid.div_b[0] || v1 >= c.grid.div_b[1] || v2 >= c.grid.div_b[2])
-                        continue;
-                    const int vox = v0 * c.grid.mul[0] + v1 * c.grid.mul[1] + v2 * c.grid.mul[2];
-                    unsigned h = hash_voxel(vox, mask);
-                    int slot = -1;
-                    for (;;) {
-                        const int key = __ldg(table_key + h);
-                        if (key == vox) {
-                            slot = __ldg(table_slot + h);
-                            break;
-                        }
-                        if (key == -1) break;
-                        h = (h + 1) & mask;
-                    }
-                    if (slot < 0) continue;
+        for (int hit = 0; hit < n_hits; ++hit) {
+                    const int slot = hits[hit];
                     const NdtLeafDev &cell = leaves[slot];
                     const float dc = l2_simple(tx, ty, tz, cell.centroid[0], cell.centroid[1], cell.centroid[2]);
                     if (!(dc < c.r2)) continue;

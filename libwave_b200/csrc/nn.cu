@@ -152,7 +152,7 @@ int wavecu_nn_create(int device, void *stream, wavecu_nn **out) {
         WCU_CHECK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
         h.own_stream = true;
     }
-    h.q.key_bits = 10;
+    h.q.key_bits = 12;
     h.tgt.cloud.device = h.q.device = device;
     h.tgt.cloud.stream = h.q.stream = h.stream;
     WCU_CHECK(cudaEventCreate(&h.e0));
