@@ -89,7 +89,12 @@ int wavecu_icp_create(const wavecu_icp_params *params, int device, void *stream,
 int wavecu_icp_destroy(wavecu_icp *h);
 int wavecu_icp_set_params(wavecu_icp *h, const wavecu_icp_params *params);
 
-/* Host clouds (borrowed for the call, copied to the device inside). */
+/* Host clouds, copied to the device.  The copy is asynchronous: it overlaps the sort / tree build of
+ * the cloud set before it, and at full resolution (res <= 0) the build of this cloud is queued
+ * right behind it.  From pageable memory the CUDA runtime stages the data before the call
+ * returns; a caller that passes page-locked memory must leave the buffer untouched until the next
+ * wavecu_icp_match / wavecu_icp_align on this handle has returned (ICPMatcher holds the caller's
+ * cloud pointers over exactly that span, src/icp.cpp:67-73). */
 int wavecu_icp_set_source(wavecu_icp *h, const float *xyzw, size_t n);
 int wavecu_icp_set_target(wavecu_icp *h, const float *xyzw, size_t n);
 /* Unit normals of the target, same order and stride as the target (point-to-plane only). */
