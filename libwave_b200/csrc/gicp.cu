@@ -31,6 +31,10 @@ namespace wavecu {
 
 namespace {
 
+struct GicpPose {
+    float T[16];
+};
+
 constexpr int kGicpThreads = 128;
 constexpr int kCostVals = 14;  // f, g_t(3), Racc(9), pair count
 
@@ -145,10 +149,12 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_corr_kernel(const float4 *_
 __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *__restrict__ src_sorted, int n_src,
                                                                  const float4 *__restrict__ tgt_sorted,
                                                                  const int *__restrict__ pos,
-                                                                 const double *__restrict__ mahal,
-                                                                 const float *__restrict__ T_dev, double *partial) {
+                                                                 const double *__restrict__ mahal, GicpPose pose,
+                                                                 double *partial, unsigned *ticket,
+                                                                 volatile double *host_sums, volatile int *host_seq,
+                                                                 int seq) {
     __shared__ float T[12];
-    if (threadIdx.x < 12) T[threadIdx.x] = T_dev[threadIdx.x];
+    if (threadIdx.x < 12) T[threadIdx.x] = pose.T[threadIdx.x];
     __syncthreads();
     double acc[kCostVals];
 #pragma unroll
@@ -187,14 +193,26 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *_
         for (int w = 0; w < kGicpThreads / 32; ++w) v += s_red[w][threadIdx.x];
         partial[(size_t) blockIdx.x * kCostVals + threadIdx.x] = v;
     }
-}
-
-__global__ void gicp_final_sum_kernel(const double *__restrict__ partial, int n_blocks, double *out) {
-    const int i = threadIdx.x;
-    if (i >= kCostVals) return;
-    double v = 0;
-    for (int b = 0; b < n_blocks; ++b) v += partial[(size_t) b * kCostVals + i];
-    out[i] = v;
+    // The last block to arrive adds the block rows in block order (the result does not depend on
+    // which block that is) and hands the 14 sums to the host through mapped memory: one launch and
+    // no copy per BFGS evaluation, of which a match makes several hundred.
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x < kCostVals) {
+        double v = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partial + (size_t) b * kCostVals + threadIdx.x);
+        host_sums[threadIdx.x] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        *host_seq = seq;
+    }
 }
 
 // covariances from sorted order back to original point order (test hook)
@@ -288,7 +306,10 @@ struct GicpHandle {
     bool cov_src_ok = false, cov_tgt_ok = false;
     GicpIterConsts *d_consts = nullptr;
     float *d_T = nullptr;
-    double *d_partial = nullptr, *d_sums = nullptr, *h_sums = nullptr;
+    double *d_partial = nullptr, *d_sums = nullptr, *h_sums = nullptr;  // h_sums: mapped host memory
+    unsigned *d_ticket = nullptr;
+    int *h_seq = nullptr;   // mapped: number of the last evaluation whose sums are in h_sums
+    int cost_seq = 0;
     int n_blocks = 148 * 4;
     long long launches = 0, evaluations = 0, inner_iterations = 0;
     size_t n_corr = 0;
@@ -308,7 +329,11 @@ struct GicpHandle {
         WCU_CHECK(cudaMalloc((void **) &d_T, 16 * sizeof(float)));
         WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(double) * kCostVals * (size_t) n_blocks));
         WCU_CHECK(cudaMalloc((void **) &d_sums, sizeof(double) * kCostVals));
-        WCU_CHECK(cudaHostAlloc((void **) &h_sums, sizeof(double) * kCostVals, cudaHostAllocDefault));
+        WCU_CHECK(cudaHostAlloc((void **) &h_sums, sizeof(double) * kCostVals, cudaHostAllocMapped));
+        WCU_CHECK(cudaHostAlloc((void **) &h_seq, sizeof(int), cudaHostAllocMapped));
+        *h_seq = 0;
+        WCU_CHECK(cudaMalloc((void **) &d_ticket, sizeof(unsigned)));
+        WCU_CHECK(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), stream));
         return WAVECU_OK;
     }
 
@@ -398,15 +423,31 @@ struct GicpHandle {
         float T[16];
         identity4(T);
         apply_state(T, x);
-        WCU_CHECK(cudaMemcpyAsync(d_T, T, sizeof T, cudaMemcpyHostToDevice, stream));
-        gicp_cost_kernel<<<n_blocks, kGicpThreads, 0, stream>>>(src.cloud.d_sorted, (int) src.cloud.n, tgt.cloud.d_sorted,
-                                                                d_pos, d_mahal, d_T, d_partial);
-        gicp_final_sum_kernel<<<1, 32, 0, stream>>>(d_partial, n_blocks, d_sums);
-        launches += 2;
+        GicpPose pose;
+        std::memcpy(pose.T, T, sizeof T);
         ++evaluations;
-        WCU_CHECK(cudaMemcpyAsync(h_sums, d_sums, sizeof(double) * kCostVals, cudaMemcpyDeviceToHost, stream));
-        WCU_CHECK(cudaStreamSynchronize(stream));
+        const int seq = ++cost_seq;
+        gicp_cost_kernel<<<n_blocks, kGicpThreads, 0, stream>>>(src.cloud.d_sorted, (int) src.cloud.n, tgt.cloud.d_sorted,
+                                                                d_pos, d_mahal, pose, d_partial, d_ticket, h_sums,
+                                                                h_seq, seq);
+        ++launches;
         WCU_CHECK(cudaGetLastError());
+        // wait for the kernel's own hand-over instead of synchronising the stream
+        for (int spins = 0; *(volatile int *) h_seq != seq;) {
+            if (++spins % 4096 == 0) {
+                const cudaError_t q = cudaStreamQuery(stream);
+                if (q != cudaErrorNotReady) {
+                    if (q != cudaSuccess) WCU_CHECK(q);
+                    if (*(volatile int *) h_seq != seq) {
+                        set_last_error("gicp_cost_kernel finished without publishing its sums");
+                        return WAVECU_ERR_CUDA;
+                    }
+                }
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
         const double m = (double) m_pairs;
         if (f) *f = h_sums[0] / m;
         if (g) {
@@ -429,6 +470,8 @@ struct GicpHandle {
                         (void *) d_pos, (void *) d_consts, (void *) d_T, (void *) d_partial, (void *) d_sums})
             if (p) cudaFree(p);
         if (h_sums) cudaFreeHost(h_sums);
+        if (h_seq) cudaFreeHost(h_seq);
+        if (d_ticket) cudaFree(d_ticket);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };

@@ -227,9 +227,9 @@ struct SolveArgs {
     int launch;
 };
 
+// (a posted store: nothing waits for it - it is visible to the host at the latest when the kernel ends)
 __device__ __forceinline__ void publish_progress(const SolveArgs &a, int done) {
     *a.progress = (a.launch << 1) | (done ? 1 : 0);
-    __threadfence_system();
 }
 
 // Rotation maximising trace(R^T S): one-sided Jacobi on S, fixed pair order, <= 12 sweeps (stops

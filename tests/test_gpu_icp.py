@@ -65,6 +65,30 @@ def test_nn_max_dist_and_edge_cases(W, oracle):
     assert (i0 == -1).all()
 
 
+@pytest.mark.parametrize("n_tgt", [1, 2, 3, 5, 9, 33])
+def test_tiny_targets_duplicates_and_ties(W, oracle, n_tgt):
+    """The tree degenerates for tiny targets (a one-point target has no node at all) and duplicated
+    target points tie exactly: the lowest target index must win, in the stand-alone search and as the
+    ICP correspondences."""
+    rng = np.random.default_rng(n_tgt)
+    base = rng.uniform(-2, 2, size=(n_tgt, 3)).astype(np.float32)
+    tgt = np.concatenate([base, base[::-1]])             # every point twice: exact ties everywhere
+    qry = rng.uniform(-3, 3, size=(257, 3)).astype(np.float32)
+    qry[:n_tgt] = base                                    # zero-distance queries too
+    idx, d2 = W.NearestNeighbour(tgt).search(qry)
+    ridx, rd2 = oracle.brute_nn1(tgt, qry)
+    assert np.array_equal(idx, ridx) and np.array_equal(d2, rd2)
+    assert (idx < n_tgt).all()                            # never the duplicate with the higher index
+    if n_tgt >= 3:
+        m = W.ICPMatcher(W.ICPMatcherParams(res=-1, max_corr=100.0, max_iter=3))
+        m.setup(qry, tgt)
+        m.match()
+        ref = oracle.icp_align(qry, tgt, max_corr=100.0, max_iter=3, sum_mode=oracle.SUM_EXACT)
+        q, mm, dd = m.correspondences()
+        assert m.iterations == ref.iterations
+        assert np.array_equal(mm, ref.corr_match) and np.array_equal(dd, ref.corr_dist)
+
+
 @pytest.mark.parametrize("tx", [0.0, 0.2])
 def test_icp_fullres_bit_exact_vs_oracle(W, oracle, testscan, tx):
     """fullResNullMatch (tests/icp_tests.cpp:45-62) and the 0.2 m displacement at full resolution."""
