@@ -305,8 +305,7 @@ struct GicpHandle {
     size_t src_cap = 0, tgt_cap = 0;
     bool cov_src_ok = false, cov_tgt_ok = false;
     GicpIterConsts *d_consts = nullptr;
-    float *d_T = nullptr;
-    double *d_partial = nullptr, *d_sums = nullptr, *h_sums = nullptr;  // h_sums: mapped host memory
+    double *d_partial = nullptr, *h_sums = nullptr;  // h_sums: mapped host memory
     unsigned *d_ticket = nullptr;
     int *h_seq = nullptr;   // mapped: number of the last evaluation whose sums are in h_sums
     int cost_seq = 0;
@@ -326,9 +325,7 @@ struct GicpHandle {
         src.cloud.device = tgt.cloud.device = vox.device = device;
         src.cloud.stream = tgt.cloud.stream = vox.stream = stream;
         WCU_CHECK(cudaMalloc((void **) &d_consts, sizeof(GicpIterConsts)));
-        WCU_CHECK(cudaMalloc((void **) &d_T, 16 * sizeof(float)));
         WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(double) * kCostVals * (size_t) n_blocks));
-        WCU_CHECK(cudaMalloc((void **) &d_sums, sizeof(double) * kCostVals));
         WCU_CHECK(cudaHostAlloc((void **) &h_sums, sizeof(double) * kCostVals, cudaHostAllocMapped));
         WCU_CHECK(cudaHostAlloc((void **) &h_seq, sizeof(int), cudaHostAllocMapped));
         *h_seq = 0;
@@ -467,7 +464,7 @@ struct GicpHandle {
         tgt.release();
         vox.release();
         for (void *p : {(void *) d_stage, (void *) d_cov_src, (void *) d_cov_tgt, (void *) d_mahal, (void *) d_cov_out,
-                        (void *) d_pos, (void *) d_consts, (void *) d_T, (void *) d_partial, (void *) d_sums})
+                        (void *) d_pos, (void *) d_consts, (void *) d_partial})
             if (p) cudaFree(p);
         if (h_sums) cudaFreeHost(h_sums);
         if (h_seq) cudaFreeHost(h_seq);

@@ -202,10 +202,14 @@ __global__ void __launch_bounds__(kNdtThreads, WCU_NDT_MINBLOCKS) ndt_derivative
                                                                      const NdtLeafDev *__restrict__ leaves,
                                                                      const int *__restrict__ table_key,
                                                                      const int *__restrict__ table_slot, unsigned mask,
-                                                                     const NdtConsts *__restrict__ kc, double *partial) {
+                                                                     const __grid_constant__ NdtConsts kc,
+                                                                     double *partial, unsigned *ticket,
+                                                                     volatile double *host_sums, volatile int *host_seq,
+                                                                     int seq) {
+    // the per-pass constants travel as a kernel argument (no upload in front of every pass)
     __shared__ NdtConsts c;
     for (int w = threadIdx.x; w < (int) (sizeof(NdtConsts) / 4); w += blockDim.x)
-        reinterpret_cast<int *>(&c)[w] = reinterpret_cast<const int *>(kc)[w];
+        reinterpret_cast<int *>(&c)[w] = reinterpret_cast<const int *>(&kc)[w];
     __syncthreads();
     double acc[kNdtVals];
 #pragma unroll
@@ -339,14 +343,25 @@ __global__ void __launch_bounds__(kNdtThreads, WCU_NDT_MINBLOCKS) ndt_derivative
         for (int w = 0; w < kNdtThreads / 32; ++w) v += s_red[w][threadIdx.x];
         partial[(size_t) blockIdx.x * kNdtVals + threadIdx.x] = v;
     }
-}
-
-__global__ void ndt_final_sum_kernel(const double *__restrict__ partial, int n_blocks, double *out) {
-    const int i = threadIdx.x;
-    if (i >= kNdtVals) return;
-    double v = 0;
-    for (int b = 0; b < n_blocks; ++b) v += partial[(size_t) b * kNdtVals + i];
-    out[i] = v;
+    // the last block to arrive adds the block rows in block order and hands the 28 sums to the host
+    // through mapped memory: one launch, no copy and no stream synchronisation per derivative pass
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x < kNdtVals) {
+        double v = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partial + (size_t) b * kNdtVals + threadIdx.x);
+        host_sums[threadIdx.x] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        *host_seq = seq;
+    }
 }
 
 // ---- host-side numerics of the optimiser (fp64) ------------------------------------------------------
@@ -530,8 +545,10 @@ struct NdtHandle {
     float resolution = 1.f;
     GridDesc grid{};
     bool grid_ok = false;
-    NdtConsts *d_consts = nullptr;
-    double *d_partial = nullptr, *d_sums = nullptr, *h_sums = nullptr;
+    double *d_partial = nullptr, *h_sums = nullptr;  // h_sums: mapped host memory
+    unsigned *d_ticket = nullptr;
+    int *h_seq = nullptr;  // mapped: number of the last pass whose sums are in h_sums
+    int pass_seq = 0;
     int n_blocks = 0;
     long long launches = 0;
     long long derivative_passes = 0;
@@ -546,10 +563,12 @@ struct NdtHandle {
         vox.device = device;
         vox.stream = stream;
         n_blocks = 148 * 4;
-        WCU_CHECK(cudaMalloc((void **) &d_consts, sizeof(NdtConsts)));
         WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(double) * kNdtVals * (size_t) n_blocks));
-        WCU_CHECK(cudaMalloc((void **) &d_sums, sizeof(double) * kNdtVals));
-        WCU_CHECK(cudaHostAlloc((void **) &h_sums, sizeof(double) * kNdtVals, cudaHostAllocDefault));
+        WCU_CHECK(cudaHostAlloc((void **) &h_sums, sizeof(double) * kNdtVals, cudaHostAllocMapped));
+        WCU_CHECK(cudaHostAlloc((void **) &h_seq, sizeof(int), cudaHostAllocMapped));
+        *h_seq = 0;
+        WCU_CHECK(cudaMalloc((void **) &d_ticket, sizeof(unsigned)));
+        WCU_CHECK(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), stream));
         return WAVECU_OK;
     }
 
@@ -622,15 +641,28 @@ struct NdtHandle {
         c.r2 = static_cast<float>((double) resolution * (double) resolution);
         c.with_hessian = with_hessian ? 1 : 0;
         c.grid = grid;
-        WCU_CHECK(cudaMemcpyAsync(d_consts, &c, sizeof c, cudaMemcpyHostToDevice, stream));
+        const int seq = ++pass_seq;
         ndt_derivative_kernel<<<n_blocks, kNdtThreads, 0, stream>>>(d_src, (int) n_src, d_leaves, d_table_key,
-                                                                     d_table_slot, table_mask, d_consts, d_partial);
-        ndt_final_sum_kernel<<<1, 32, 0, stream>>>(d_partial, n_blocks, d_sums);
-        launches += 2;
+                                                                     d_table_slot, table_mask, c, d_partial, d_ticket,
+                                                                     h_sums, h_seq, seq);
+        ++launches;
         ++derivative_passes;
-        WCU_CHECK(cudaMemcpyAsync(h_sums, d_sums, sizeof(double) * kNdtVals, cudaMemcpyDeviceToHost, stream));
-        WCU_CHECK(cudaStreamSynchronize(stream));
         WCU_CHECK(cudaGetLastError());
+        for (int spins = 0; *(volatile int *) h_seq != seq;) {  // the kernel's own hand-over
+            if (++spins % 4096 == 0) {
+                const cudaError_t q = cudaStreamQuery(stream);
+                if (q != cudaErrorNotReady) {
+                    if (q != cudaSuccess) WCU_CHECK(q);
+                    if (*(volatile int *) h_seq != seq) {
+                        set_last_error("ndt_derivative_kernel finished without publishing its sums");
+                        return WAVECU_ERR_CUDA;
+                    }
+                }
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
         *score = h_sums[0];
         for (int i = 0; i < 6; ++i) g[i] = h_sums[1 + i];
         if (with_hessian) {
@@ -761,9 +793,11 @@ struct NdtHandle {
         cudaSetDevice(device);
         vox.release();
         for (void *p : {(void *) d_src, (void *) d_tgt, (void *) d_leaves, (void *) d_table_key, (void *) d_table_slot,
-                        (void *) d_consts, (void *) d_partial, (void *) d_sums})
+                        (void *) d_partial})
             if (p) cudaFree(p);
         if (h_sums) cudaFreeHost(h_sums);
+        if (h_seq) cudaFreeHost(h_seq);
+        if (d_ticket) cudaFree(d_ticket);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };

