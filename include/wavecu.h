@@ -94,7 +94,9 @@ int wavecu_icp_set_params(wavecu_icp *h, const wavecu_icp_params *params);
  * right behind it.  From pageable memory the CUDA runtime stages the data before the call
  * returns; a caller that passes page-locked memory must leave the buffer untouched until the next
  * wavecu_icp_match / wavecu_icp_align on this handle has returned (ICPMatcher holds the caller's
- * cloud pointers over exactly that span, src/icp.cpp:67-73). */
+ * cloud pointers over exactly that span, src/icp.cpp:67-73).  A page-locked source is in fact
+ * copied behind the target set after it: the first iteration waits for the target's tree, not for
+ * the source. */
 int wavecu_icp_set_source(wavecu_icp *h, const float *xyzw, size_t n);
 int wavecu_icp_set_target(wavecu_icp *h, const float *xyzw, size_t n);
 /* Unit normals of the target, same order and stride as the target (point-to-plane only). */

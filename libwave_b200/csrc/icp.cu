@@ -134,6 +134,11 @@ struct IcpHandle {
     TargetIndex tgt;
     bool src_dirty = true;
     bool src_sorted_fresh = false;   // src.d_sorted holds an unconsumed Morton sort of the uploaded source
+    // A page-locked host source is not copied at once: setRef comes before setTarget, but it is the target
+    // whose tree the first iteration waits for, so its copy goes first and the source follows it
+    // (flushed by set_target, or by whatever needs the source next).
+    const float *pending_src = nullptr;
+    size_t pending_src_n = 0;
 
     // iteration buffers
     int *d_nn_pos = nullptr, *d_nn_idx = nullptr;
@@ -185,6 +190,7 @@ struct IcpHandle {
     int on_set_source(bool from_device);
     int on_set_target(bool from_device);
     int set_source(const float *xyzw, size_t n, bool from_device);
+    int flush_pending_source();
     int set_target(const float *xyzw, size_t n, bool from_device);
     int set_target_normals(const float *nxyzw, size_t n, bool from_device);
     int mark_first();
@@ -283,9 +289,36 @@ int IcpHandle::set_source(const float *xyzw, size_t n, bool from_device) {
     WCU_CHECK(cudaSetDevice(device));
     int rc = on_set_source(from_device);
     if (rc) return rc;
+    pending_src = nullptr;
+    if (!from_device && n) {
+        // the caller keeps page-locked buffers untouched until match() returns (wavecu.h): defer
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, xyzw) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+            pending_src = xyzw;
+            pending_src_n = n;
+            return WAVECU_OK;
+        }
+        cudaGetLastError();
+    }
     rc = src.upload(xyzw, n, from_device);
     if (rc) return rc;
     if (!(prm.res > 0) && n) {  // full resolution: this cloud is the working cloud - sort it right away
+        rc = src.sort(n);
+        if (rc) return rc;
+        WCU_CHECK(cudaEventRecord(ev_src_sorted, aux));
+        src_sorted_fresh = true;
+    }
+    return WAVECU_OK;
+}
+
+int IcpHandle::flush_pending_source() {
+    if (!pending_src) return WAVECU_OK;
+    const float *p = pending_src;
+    const size_t n = pending_src_n;
+    pending_src = nullptr;
+    int rc = src.upload(p, n, false);
+    if (rc) return rc;
+    if (!(prm.res > 0) && n) {
         rc = src.sort(n);
         if (rc) return rc;
         WCU_CHECK(cudaEventRecord(ev_src_sorted, aux));
@@ -300,8 +333,11 @@ int IcpHandle::set_target(const float *xyzw, size_t n, bool from_device) {
     if (rc) return rc;
     rc = tgt.set_points(xyzw, n, from_device);
     if (rc) return rc;
-    if (!(prm.res > 0) && n) return tgt.build();  // full resolution: build the search tree behind the copy
-    return WAVECU_OK;
+    if (!(prm.res > 0) && n) {  // full resolution: build the search tree behind the copy
+        rc = tgt.build();
+        if (rc) return rc;
+    }
+    return flush_pending_source();  // the deferred source copy goes behind the target's
 }
 
 int IcpHandle::set_target_normals(const float *nxyzw, size_t n, bool from_device) {
@@ -338,6 +374,10 @@ int IcpHandle::ensure_iter_buffers(size_t n_src_pad, int max_iter) {
 
 int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state) {
     WCU_CHECK(cudaSetDevice(device));
+    {
+        const int rc = flush_pending_source();
+        if (rc) return rc;
+    }
     have_result = false;
     const size_t n_src = src.n, n_tgt = tgt.cloud.n;
     const int max_iter = std::max(prm.max_iter, 1);
@@ -361,6 +401,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         WCU_CHECK(cudaEventRecord(e_begin, stream));
     }
 
+    bool late_normals = false;
     // ---- build: Morton-sort both clouds, AABB tree over the target ----
     const size_t n_src_pad = n_src;
     int rc = ensure_iter_buffers(std::max<size_t>(n_src_pad, 1), max_iter);
@@ -380,10 +421,11 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     }
     if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
         if (tgt.nrm_n == n_tgt) {
-            if (tgt.nrm_dirty) {
-                rc = tgt.sort_normals();
-                if (rc) return rc;
-            }
+            // the caller's normals are only read by the first reduction: their gather into Morton order is
+            // queued behind the first correspondence launch, so that search does not wait for their upload
+            late_normals = tgt.nrm_dirty;
+            rc = tgt.reserve_sorted_normals();
+            if (rc) return rc;
         } else if (!tgt.normals_estimated) {
             // no normals from the caller: estimate them on the target's own tree (k = 10 neighbours)
             rc = tgt.estimate_normals(10);
@@ -435,6 +477,11 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         if (profiling) {
             it_ev.push_back(next_event());
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
+        }
+        if (late_normals) {
+            late_normals = false;
+            rc = tgt.sort_normals();
+            if (rc) return rc;
         }
         so.launch = k + 1;
         if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
@@ -607,6 +654,10 @@ int IcpHandle::load_level(float leaf, const double *running) {
 
 int IcpHandle::match(double *T_out, int *converged, int *iterations) {
     WCU_CHECK(cudaSetDevice(device));
+    {
+        const int rc = flush_pending_source();
+        if (rc) return rc;
+    }
     if (converged) *converged = 0;
     if (iterations) *iterations = 0;
     if (!(prm.res > 0)) {

@@ -478,6 +478,17 @@ __global__ void __launch_bounds__(kBuildThreads) gather_extra_kernel(const float
 }
 }  // namespace
 
+int TargetIndex::reserve_sorted_normals() {
+    const size_t n = cloud.n;
+    if (n > nrm_sorted_cap) {
+        if (d_nrm_sorted) WCU_CHECK(cudaFree(d_nrm_sorted));
+        d_nrm_sorted = nullptr;
+        WCU_CHECK(cudaMalloc((void **) &d_nrm_sorted, (n + n / 8 + 64) * sizeof(float4)));
+        nrm_sorted_cap = n + n / 8 + 64;
+    }
+    return WAVECU_OK;
+}
+
 int TargetIndex::sort_normals() {
     WCU_CHECK(cudaSetDevice(cloud.device));
     const size_t n = cloud.n;
@@ -485,12 +496,8 @@ int TargetIndex::sort_normals() {
         nrm_dirty = false;
         return WAVECU_OK;
     }
-    if (n > nrm_sorted_cap) {
-        if (d_nrm_sorted) WCU_CHECK(cudaFree(d_nrm_sorted));
-        d_nrm_sorted = nullptr;
-        WCU_CHECK(cudaMalloc((void **) &d_nrm_sorted, (n + n / 8 + 64) * sizeof(float4)));
-        nrm_sorted_cap = n + n / 8 + 64;
-    }
+    const int rc = reserve_sorted_normals();
+    if (rc) return rc;
     if (cloud.copy_stream && nrm_up_pending) WCU_CHECK(cudaStreamWaitEvent(cloud.stream, ev_nrm_up, 0));
     if (n) {
         gather_extra_kernel<<<(unsigned) ((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, cloud.stream>>>(

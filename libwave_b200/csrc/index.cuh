@@ -113,6 +113,7 @@ struct TargetIndex {
     int enqueue_build();
     GraphCache build_graph;
     int sort_normals();      // d_nrm_sorted <- d_nrm_raw in the Morton order of the last build
+    int reserve_sorted_normals();
     cudaEvent_t ev_nrm_up = nullptr;
     bool nrm_up_pending = false, nrm_dirty = false;
     // fills d_nrm_sorted with unit normals estimated from the k nearest neighbours of every target
