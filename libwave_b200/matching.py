@@ -117,16 +117,21 @@ class ICPMatcher(Matcher):
 
     # -- clouds ----------------------------------------------------------------------------------
     def setRef(self, ref):
+        """(n, 3) or (n, 4) float32.  A page-locked (n, 4) array is handed to the library as it is and
+        copied asynchronously: keep it alive and unmodified until match() has returned (wavecu.h)."""
         a = _xyzw(ref)
         self._n_ref = a.shape[0]
+        self._keep_ref = a          # the upload may still be pending when this method returns
         capi.check(self._L.wavecu_icp_set_source(self._h, _f(a), a.shape[0]))
 
     def setTarget(self, target):
         a = _xyzw(target)
+        self._keep_tgt = a
         capi.check(self._L.wavecu_icp_set_target(self._h, _f(a), a.shape[0]))
 
     def setTargetNormals(self, normals):
         a = _xyzw(normals)
+        self._keep_nrm = a
         capi.check(self._L.wavecu_icp_set_target_normals(self._h, _f(a), a.shape[0]))
 
     def setRefDevice(self, ptr: int, n: int):
