@@ -121,10 +121,29 @@ __device__ __forceinline__ bool gap_less(const unsigned long long *__restrict__ 
 // box and link into that parent's record, then exchanges its far bound through other[parent]:
 // the first child to arrive retires, the second continues upward with the merged range and box.
 // Subtrees of <= kLeaf points are referenced as leaves (runs of the sorted array).
+// number of leading key bits (of the 3 * bits Morton bits) two sorted keys share
+__device__ __forceinline__ int shared_prefix(unsigned long long a, unsigned long long b, int bits) {
+    const unsigned long long x = a ^ b;
+    return x ? __clzll((long long) x) - (64 - 3 * bits) : 3 * bits;
+}
+
+// (cx, cy, cz) of the coarse cell of a Morton key -> linear index
+__device__ __forceinline__ unsigned cell_of_key(unsigned long long key, int bits) {
+    const unsigned long long c = key >> (3 * (bits - kCellBits));  // 3 * kCellBits interleaved bits, x lowest
+    unsigned cx = 0, cy = 0, cz = 0;
+#pragma unroll
+    for (int b = 0; b < kCellBits; ++b) {
+        cx |= (unsigned) ((c >> (3 * b)) & 1ull) << b;
+        cy |= (unsigned) ((c >> (3 * b + 1)) & 1ull) << b;
+        cz |= (unsigned) ((c >> (3 * b + 2)) & 1ull) << b;
+    }
+    return cx | (cy << kCellBits) | (cz << (2 * kCellBits));
+}
+
 __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long long *__restrict__ keys,
                                                              const float4 *__restrict__ pts,
                                                              const unsigned *__restrict__ bbox, TNode *nodes, int *other,
-                                                             TreeRoot *root) {
+                                                             TreeRoot *root, CellEntry *cells, int bits) {
     const int n = (int) bbox[6];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && n == 0) {
@@ -137,10 +156,20 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
     float lox = p.x, loy = p.y, loz = p.z, hix = p.x, hiy = p.y, hiz = p.z;
     int link = make_leaf_link(i, 1);
     float tag = p.w;  // a single-point child carries the point's original index in hi.w
+    bool below = cells != nullptr;  // this node still lies inside one coarse cell
     for (;;) {
+        // The keys of [l, r] share `own` leading bits; the node is the root of a coarse cell when that is
+        // at least the cell prefix and its parent's shared prefix is shorter.  Once a node is above the
+        // cell level so are all its ancestors: the long upper part of the climb skips the key loads.
+        int own = 0;
+        if (below) {
+            own = shared_prefix(keys[l], keys[r], bits);
+            below = own >= 3 * kCellBits;
+        }
         if (l == 0 && r == n - 1) {
             root->lo = make_float4(lox, loy, loz, __int_as_float(link));
             root->hi = make_float4(hix, hiy, hiz, __int_as_float(r - l + 1));
+            if (below) cells[cell_of_key(keys[l], bits)] = link;
             return;
         }
         bool parent_right;  // parent is gap r: this node is its left child
@@ -148,6 +177,8 @@ __global__ void __launch_bounds__(kBuildThreads) lbvh_kernel(const unsigned long
         else if (r == n - 1) parent_right = false;
         else parent_right = gap_less(keys, r, l - 1);
         const int par = parent_right ? r : l - 1;
+        if (below && shared_prefix(keys[par], keys[par + 1], bits) < 3 * kCellBits)
+            cells[cell_of_key(keys[l], bits)] = link;
         TNode *nd = nodes + par;
         if (parent_right) {
             nd->lo0 = make_float4(lox, loy, loz, __int_as_float(link));
@@ -527,6 +558,7 @@ int TargetIndex::build() {
         node_cap = a;
     }
     if (!d_root) WCU_CHECK(cudaMalloc((void **) &d_root, sizeof(TreeRoot)));
+    if (kCellBits > 0 && !d_cells) WCU_CHECK(cudaMalloc((void **) &d_cells, kCellCount * sizeof(CellEntry)));
     int rc = cloud.pre_sort(std::max<size_t>(n, 1));
     if (rc) return rc;
     const unsigned long long key[8] = {(unsigned long long) n, (unsigned long long) (uintptr_t) cloud.d_raw,
@@ -550,8 +582,11 @@ int TargetIndex::enqueue_build() {
     int rc = cloud.enqueue_sort(std::max<size_t>(n, 1), nullptr, nullptr);
     if (rc) return rc;
     if (n) WCU_CHECK(cudaMemsetAsync(d_other, 0xff, n * sizeof(int), cloud.stream));
+    CellEntry *cells = (kCellBits > 0 && cloud.key_bits >= kCellBits) ? d_cells : nullptr;
+    if (cells) WCU_CHECK(cudaMemsetAsync(cells, 0x80, kCellCount * sizeof(CellEntry), cloud.stream));  // kCellEmpty
     lbvh_kernel<<<(unsigned) std::max<size_t>(1, (n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0,
-                  cloud.stream>>>(cloud.d_keys_sorted, cloud.d_sorted, cloud.d_bbox, d_nodes, d_other, d_root);
+                  cloud.stream>>>(cloud.d_keys_sorted, cloud.d_sorted, cloud.d_bbox, d_nodes, d_other, d_root, cells,
+                                  cloud.key_bits);
     ++cloud.launches;
     WCU_CHECK(cudaGetLastError());
     return WAVECU_OK;
@@ -579,8 +614,10 @@ int TargetIndex::estimate_normals(int k) {
 void TargetIndex::release() {
     build_graph.release();
     cloud.release();
-    for (void *p : {(void *) d_nodes, (void *) d_other, (void *) d_root, (void *) d_nrm_raw, (void *) d_nrm_sorted})
+    for (void *p : {(void *) d_nodes, (void *) d_other, (void *) d_root, (void *) d_nrm_raw, (void *) d_nrm_sorted,
+                    (void *) d_cells})
         if (p) cudaFree(p);
+    d_cells = nullptr;
     if (ev_nrm_up) cudaEventDestroy(ev_nrm_up);
     ev_nrm_up = nullptr;
     nrm_up_pending = nrm_dirty = false;

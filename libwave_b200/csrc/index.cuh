@@ -93,6 +93,19 @@ struct QuantParams {
     int bits;
 };
 
+// Entry table of the tree: for every cell of the coarsest 2^kCellBits^3 Morton grid, the link of
+// the subtree (or single point) that holds exactly the target points of that cell; kCellEmpty
+// (memset 0x80) for a cell without points.  A search whose ball lies inside a few cells starts at
+// their entries instead of walking the ~10 levels above them, most of which only split empty space
+// around the dense part of a lidar scan.
+#ifndef WCU_CELL_BITS
+#define WCU_CELL_BITS 7
+#endif
+constexpr int kCellBits = WCU_CELL_BITS;  // 0: no table
+constexpr size_t kCellCount = kCellBits > 0 ? (size_t) 1 << (3 * kCellBits) : 1;
+typedef int CellEntry;
+constexpr int kCellEmpty = (int) 0x80808080;  // < every leaf link (those are >= -2^27)
+
 struct TreeRoot {
     float4 lo, hi;   // box of all finite points; lo.w = link (int bits), hi.w = count (int bits)
 };
@@ -102,6 +115,7 @@ struct TargetIndex {
     TNode *d_nodes = nullptr;    // n-1 records, indexed by split position
     int *d_other = nullptr;      // n-1 rendezvous slots of the bottom-up build
     TreeRoot *d_root = nullptr;
+    CellEntry *d_cells = nullptr;   // kCellCount entries, rebuilt with the tree
     float4 *d_nrm_raw = nullptr, *d_nrm_sorted = nullptr;  // optional normals
     size_t nrm_n = 0;
     size_t node_cap = 0, nrm_cap = 0, nrm_sorted_cap = 0;
@@ -200,6 +214,10 @@ struct NnIndex {
     const TNode *nodes;
     const TreeRoot *root;
     const float4 *pts;                   // Morton-sorted, w = original index
+    const CellEntry *cells;              // entry table (kCellBits per axis), or nullptr
+    const unsigned long long *keys;      // sorted Morton keys of pts (finite points first)
+    const unsigned *bbox;                // quantisation frame of the Morton keys; [6] = number of finite points
+    int key_bits;
 };
 
 // Ordered top-down search of the subtree under internal node `link` (its box is already known to
@@ -216,27 +234,27 @@ constexpr int kLinkPop = (int) 0x80000001;  // dead end; leaf links are >= -2^30
 // subtree pops one stack entry per round; a stale entry (bound tightened since the push) just costs
 // that lane one idle round.  Every lane of a warp therefore runs the same few instructions per
 // round, whatever mix of descending, point testing and popping the lanes are in.
-__device__ __forceinline__ void subtree_search(float qx, float qy, float qz, const TNode *__restrict__ nodes,
-                                               const float4 *__restrict__ pts, int link, float &best, int &best_idx,
-                                               int &best_pos) {
-    (void) pts;
-    // (box bound, link bits) entries; the newest one lives in registers, so a pop needs no load on
-    // its critical path (the entry below it is fetched from local memory for the *next* pop).  The
-    // bottom of the stack is a sentinel that no bound admits.
-    float2 stack[kStackDepth];
-    float2 top = make_float2(INFINITY, __int_as_float(kLinkDone));
-    int sp = 0;
-    // distances are >= 0, so (distance bits, original index) compares as one unsigned 64-bit key:
-    // "closer, or as close with a lower index"
-    unsigned long long best_key = ((unsigned long long) __float_as_uint(best) << 32) | (unsigned) best_idx;
+// distances are >= 0, so (distance bits, original index) compares as one unsigned 64-bit key:
+// "closer, or as close with a lower index"
+__device__ __forceinline__ unsigned long long nn_key(float d2, unsigned idx) {
+    return ((unsigned long long) __float_as_uint(d2) << 32) | idx;
+}
+__device__ __forceinline__ float key_bound(unsigned long long key) { return __uint_as_float((unsigned) (key >> 32)); }
+
+// The walk proper.  `link`: the first node to step into (kLinkPop: start by popping).  The stack holds
+// (box bound, link bits) entries; its newest entry `top` lives in registers, so a pop needs no load on
+// its critical path (the entry below it is fetched from local memory for the *next* pop), and its
+// bottom is a sentinel that no bound admits.  (slots / top / sp are separate objects on purpose: a
+// struct holding the dynamically indexed array would be placed in local memory as a whole.)
+__device__ __forceinline__ void walk(float qx, float qy, float qz, const TNode *__restrict__ nodes, int link,
+                                     float2 *slots, float2 &top, int &sp, unsigned long long &best_key, int &best_pos) {
     for (;;) {
         if (link >= 0) {
             const float4 a = __ldg(&nodes[link].lo0), b = __ldg(&nodes[link].hi0);
             const float4 c = __ldg(&nodes[link].lo1), d = __ldg(&nodes[link].hi1);
             const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
             const int l0 = __float_as_int(a.w), l1 = __float_as_int(c.w);
-            const unsigned long long k0 = ((unsigned long long) __float_as_uint(d0) << 32) | __float_as_uint(b.w);
-            const unsigned long long k1 = ((unsigned long long) __float_as_uint(d1) << 32) | __float_as_uint(d.w);
+            const unsigned long long k0 = nn_key(d0, __float_as_uint(b.w)), k1 = nn_key(d1, __float_as_uint(d.w));
             if (l0 < 0 && k0 < best_key) {
                 best_key = k0;
                 best_pos = ~l0;
@@ -245,11 +263,11 @@ __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, con
                 best_key = k1;
                 best_pos = ~l1;
             }
-            const float bound = __uint_as_float((unsigned) (best_key >> 32));
+            const float bound = key_bound(best_key);
             const bool in0 = l0 >= 0 && d0 <= bound, in1 = l1 >= 0 && d1 <= bound;
             if (in0 && in1) {
                 const bool right_first = d1 < d0;
-                stack[sp++] = top;
+                slots[sp++] = top;
                 top = right_first ? make_float2(d0, a.w) : make_float2(d1, c.w);
                 link = right_first ? l1 : l0;
             } else {
@@ -259,11 +277,22 @@ __device__ __forceinline__ void subtree_search(float qx, float qy, float qz, con
         if (link < 0) {
             const int tl = __float_as_int(top.y);
             if (tl == kLinkDone) break;
-            link = (top.x <= __uint_as_float((unsigned) (best_key >> 32))) ? tl : kLinkPop;
-            top = stack[--sp];
+            link = (top.x <= key_bound(best_key)) ? tl : kLinkPop;
+            top = slots[--sp];
         }
     }
-    best = __uint_as_float((unsigned) (best_key >> 32));
+}
+
+__device__ __forceinline__ void subtree_search(float qx, float qy, float qz, const TNode *__restrict__ nodes,
+                                               const float4 *__restrict__ pts, int link, float &best, int &best_idx,
+                                               int &best_pos) {
+    (void) pts;
+    float2 slots[kStackDepth];
+    float2 top = make_float2(INFINITY, __int_as_float(kLinkDone));
+    int sp = 0;
+    unsigned long long best_key = nn_key(best, (unsigned) best_idx);
+    walk(qx, qy, qz, nodes, link, slots, top, sp, best_key, best_pos);
+    best = key_bound(best_key);
     best_idx = (int) (unsigned) best_key;
 }
 #else
@@ -309,6 +338,10 @@ inline NnIndex TargetIndex::index() const {
     ix.nodes = d_nodes;
     ix.root = d_root;
     ix.pts = cloud.d_sorted;
+    ix.cells = (kCellBits > 0 && cloud.key_bits >= kCellBits) ? d_cells : nullptr;
+    ix.keys = cloud.d_keys_sorted;
+    ix.bbox = cloud.d_bbox;
+    ix.key_bits = cloud.key_bits;
     return ix;
 }
 
@@ -413,5 +446,104 @@ __device__ __forceinline__ void nn_search(float qx, float qy, float qz, const Nn
     }
     subtree_search(qx, qy, qz, ix.nodes, ix.pts, root_link, best, best_idx, best_pos);
 }
+
+#if WCU_LEAF == 1
+// A candidate for a query that has none: the two sorted target points around the query's own
+// Morton key (lower_bound in the sorted key array).  Any target point is a valid candidate, so this
+// only tightens the bound; it never decides the result.
+__device__ __forceinline__ void seed_from_morton(float qx, float qy, float qz, const NnIndex &ix, const QuantParams &qp,
+                                                 float &best, int &best_idx, int &best_pos) {
+    const int n = (int) __ldg(ix.bbox + 6);
+    if (n <= 0) return;
+    const unsigned long long key = morton_code(qp, qx, qy, qz);
+    int lo = 0, hi = n;  // first position with keys[pos] >= key
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(ix.keys + mid) < key) lo = mid + 1;
+        else hi = mid;
+    }
+#pragma unroll
+    for (int j = -1; j <= 0; ++j) {
+        const int pos = min(max(lo + j, 0), n - 1);
+        const float4 p = __ldg(ix.pts + pos);
+        const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+        const int idx = __float_as_int(p.w);
+        if (d < best || (d == best && idx < best_idx)) {
+            best = d;
+            best_idx = idx;
+            best_pos = pos;
+        }
+    }
+}
+
+#ifndef WCU_SEED
+#define WCU_SEED 1
+#endif
+
+// 1-NN through the entry table.  A query with a candidate (best = its distance, best_pos >= 0; a
+// query without one is first given a seed) has a ball that usually spans at most two coarse cells
+// per axis, and every target point inside the ball then lives under the entries of those <= 8
+// cells (the quantisation behind the Morton keys is monotone per axis, and the radius is grown by
+// more than the fp32 rounding of the per-axis gaps) - so the walk starts there, the query's own cell
+// first.  Wider balls, and targets without a table, start at the root.
+__device__ __forceinline__ void nn_search_cells(float qx, float qy, float qz, const NnIndex &ix, float &best,
+                                                int &best_idx, int &best_pos) {
+    const float4 rlo = __ldg(&ix.root->lo), rhi = __ldg(&ix.root->hi);
+    if (__float_as_int(rhi.w) <= 0) return;
+    const int root_link = __float_as_int(rlo.w);
+    if (root_link < 0 || ix.cells == nullptr) {
+        nn_search(qx, qy, qz, ix, best, best_idx, best_pos);
+        return;
+    }
+    const QuantParams qp = make_quant(ix.bbox, ix.key_bits);
+    if (WCU_SEED && best_pos < 0) seed_from_morton(qx, qy, qz, ix, qp, best, best_idx, best_pos);
+    float2 slots[kStackDepth];
+    float2 top = make_float2(INFINITY, __int_as_float(kLinkDone));
+    int sp = 0;
+    unsigned long long best_key = nn_key(best, (unsigned) best_idx);
+    int link = kLinkPop;
+    const float r = sqrtf(best) * 1.00001f + fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) * 1e-6f + 1e-30f;
+    const int shift = ix.key_bits - kCellBits;
+    const int ax = (int) (quant_axis(qx - r, qp.lx, qp.scale, qp.qmax) >> shift), bx = (int) (quant_axis(qx + r, qp.lx, qp.scale, qp.qmax) >> shift);
+    const int ay = (int) (quant_axis(qy - r, qp.ly, qp.scale, qp.qmax) >> shift), by = (int) (quant_axis(qy + r, qp.ly, qp.scale, qp.qmax) >> shift);
+    const int az = (int) (quant_axis(qz - r, qp.lz, qp.scale, qp.qmax) >> shift), bz = (int) (quant_axis(qz + r, qp.lz, qp.scale, qp.qmax) >> shift);
+    if (best_pos < 0 || bx - ax > 1 || by - ay > 1 || bz - az > 1) {
+        if (aabb_dist(qx, qy, qz, rlo, rhi) <= best) link = root_link;
+    } else {
+        // the query's own cell goes last = ends up as the first link (or on top of the stack)
+        const int ox = (int) (quant_axis(qx, qp.lx, qp.scale, qp.qmax) >> shift), oy = (int) (quant_axis(qy, qp.ly, qp.scale, qp.qmax) >> shift),
+                  oz = (int) (quant_axis(qz, qp.lz, qp.scale, qp.qmax) >> shift);
+        const int own = ox | (oy << kCellBits) | (oz << (2 * kCellBits));
+        auto enter = [&](int cell) {
+            const int l = __ldg(ix.cells + cell);
+            if (l == kCellEmpty) return;
+            if (l < 0) {  // a single point
+                const float4 p = __ldg(ix.pts + ~l);
+                const unsigned long long k = nn_key(l2_simple(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
+                if (k < best_key) {
+                    best_key = k;
+                    best_pos = ~l;
+                }
+                return;
+            }
+            if (link >= 0) {
+                slots[sp++] = top;
+                top = make_float2(0.0f, __int_as_float(link));  // bound 0: always admitted; its node step prunes
+            }
+            link = l;
+        };
+        for (int cz = az; cz <= bz; ++cz)
+            for (int cy = ay; cy <= by; ++cy)
+                for (int cx = ax; cx <= bx; ++cx) {
+                    const int cell = cx | (cy << kCellBits) | (cz << (2 * kCellBits));
+                    if (cell != own) enter(cell);
+                }
+        enter(own);
+    }
+    walk(qx, qy, qz, ix.nodes, link, slots, top, sp, best_key, best_pos);
+    best = key_bound(best_key);
+    best_idx = (int) (unsigned) best_key;
+}
+#endif
 
 }  // namespace wavecu
