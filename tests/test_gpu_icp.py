@@ -89,6 +89,41 @@ def test_tiny_targets_duplicates_and_ties(W, oracle, n_tgt):
         assert np.array_equal(mm, ref.corr_match) and np.array_equal(dd, ref.corr_dist)
 
 
+@pytest.mark.parametrize("shape", ["slab", "line", "clusters", "far_queries"])
+def test_entry_table_adversarial_geometry(W, oracle, shape):
+    """The entry table (coarse Morton cells -> subtrees) and the Morton-key seeds must not change a single
+    correspondence: degenerate extents, clustered duplicates, queries far outside the target box and
+    bounds that span many cells, checked bit for bit against the oracle over several iterations."""
+    rng = np.random.default_rng({"slab": 1, "line": 2, "clusters": 3, "far_queries": 4}[shape])
+    n = 6000
+    if shape == "slab":          # 200 m x 150 m x 2 cm
+        tgt = rng.uniform([-100, -75, -0.01], [100, 75, 0.01], size=(n, 3))
+    elif shape == "line":        # zero extent on two axes
+        tgt = np.zeros((n, 3))
+        tgt[:, 0] = rng.uniform(-50, 50, n)
+    elif shape == "clusters":    # a few tight clusters plus exact duplicates
+        centers = rng.uniform(-60, 60, size=(12, 3))
+        tgt = centers[rng.integers(0, 12, n)] + rng.normal(0, 0.02, (n, 3))
+        tgt[n // 2:] = tgt[: n - n // 2]
+    else:
+        tgt = rng.uniform(-5, 5, size=(n, 3))
+    tgt = tgt.astype(np.float32)
+    src = (tgt[rng.permutation(n)] + rng.normal(0, 0.3, (n, 3))).astype(np.float32)
+    if shape == "far_queries":
+        src[::7] += np.float32(40.0)             # far outside the target's bounding box
+    src[::11] += rng.uniform(-2.5, 2.5, (len(src[::11]), 3)).astype(np.float32)
+    kw = dict(max_corr=5.0 if shape != "far_queries" else 100.0, max_iter=5)
+    m = W.ICPMatcher(W.ICPMatcherParams(res=-1, **kw))
+    m.setup(src, tgt)
+    m.match()
+    ref = oracle.icp_align(src, tgt, sum_mode=oracle.SUM_EXACT, nn_threads=8, **kw)
+    q, mm, dd = m.correspondences()
+    assert m.iterations == ref.iterations
+    assert np.array_equal(q, ref.corr_query) and np.array_equal(mm, ref.corr_match) and np.array_equal(dd, ref.corr_dist)
+    if ref.converged:
+        assert np.array_equal(m.getResult().astype(np.float32), ref.T)
+
+
 @pytest.mark.parametrize("tx", [0.0, 0.2])
 def test_icp_fullres_bit_exact_vs_oracle(W, oracle, testscan, tx):
     """fullResNullMatch (tests/icp_tests.cpp:45-62) and the 0.2 m displacement at full resolution."""
