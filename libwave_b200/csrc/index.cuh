@@ -215,8 +215,7 @@ struct NnIndex {
     const TreeRoot *root;
     const float4 *pts;                   // Morton-sorted, w = original index
     const CellEntry *cells;              // entry table (kCellBits per axis), or nullptr
-    const unsigned long long *keys;      // sorted Morton keys of pts (finite points first)
-    const unsigned *bbox;                // quantisation frame of the Morton keys; [6] = number of finite points
+    const unsigned *bbox;                // quantisation frame of the Morton keys
     int key_bits;
 };
 
@@ -339,7 +338,6 @@ inline NnIndex TargetIndex::index() const {
     ix.root = d_root;
     ix.pts = cloud.d_sorted;
     ix.cells = (kCellBits > 0 && cloud.key_bits >= kCellBits) ? d_cells : nullptr;
-    ix.keys = cloud.d_keys_sorted;
     ix.bbox = cloud.d_bbox;
     ix.key_bits = cloud.key_bits;
     return ix;
@@ -448,44 +446,14 @@ __device__ __forceinline__ void nn_search(float qx, float qy, float qz, const Nn
 }
 
 #if WCU_LEAF == 1
-// A candidate for a query that has none: the two sorted target points around the query's own
-// Morton key (lower_bound in the sorted key array).  Any target point is a valid candidate, so this
-// only tightens the bound; it never decides the result.
-__device__ __forceinline__ void seed_from_morton(float qx, float qy, float qz, const NnIndex &ix, const QuantParams &qp,
-                                                 float &best, int &best_idx, int &best_pos) {
-    const int n = (int) __ldg(ix.bbox + 6);
-    if (n <= 0) return;
-    const unsigned long long key = morton_code(qp, qx, qy, qz);
-    int lo = 0, hi = n;  // first position with keys[pos] >= key
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(ix.keys + mid) < key) lo = mid + 1;
-        else hi = mid;
-    }
-#pragma unroll
-    for (int j = -1; j <= 0; ++j) {
-        const int pos = min(max(lo + j, 0), n - 1);
-        const float4 p = __ldg(ix.pts + pos);
-        const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
-        const int idx = __float_as_int(p.w);
-        if (d < best || (d == best && idx < best_idx)) {
-            best = d;
-            best_idx = idx;
-            best_pos = pos;
-        }
-    }
-}
-
-#ifndef WCU_SEED
-#define WCU_SEED 1
-#endif
-
-// 1-NN through the entry table.  A query with a candidate (best = its distance, best_pos >= 0; a
-// query without one is first given a seed) has a ball that usually spans at most two coarse cells
-// per axis, and every target point inside the ball then lives under the entries of those <= 8
-// cells (the quantisation behind the Morton keys is monotone per axis, and the radius is grown by
-// more than the fp32 rounding of the per-axis gaps) - so the walk starts there, the query's own cell
-// first.  Wider balls, and targets without a table, start at the root.
+// 1-NN through the entry table.  A query with a candidate (best = its distance, best_pos >= 0) has
+// a ball that usually spans at most two coarse cells per axis, and every target point inside the
+// ball then lives under the entries of those <= 8 cells (the quantisation behind the Morton keys is
+// monotone per axis, and the radius is grown by more than the fp32 rounding of the per-axis gaps) -
+// so the walk starts there, the query's own cell first.  A query without a candidate first searches
+// its own cell's subtree, which is exact for that cell and usually yields the neighbour or a tight
+// bound, and then only has the other cells of its ball left.  Wider balls, and targets without a
+// table, start at the root.
 __device__ __forceinline__ void nn_search_cells(float qx, float qy, float qz, const NnIndex &ix, float &best,
                                                 int &best_idx, int &best_pos) {
     const float4 rlo = __ldg(&ix.root->lo), rhi = __ldg(&ix.root->hi);
@@ -496,49 +464,57 @@ __device__ __forceinline__ void nn_search_cells(float qx, float qy, float qz, co
         return;
     }
     const QuantParams qp = make_quant(ix.bbox, ix.key_bits);
-    if (WCU_SEED && best_pos < 0) seed_from_morton(qx, qy, qz, ix, qp, best, best_idx, best_pos);
+    const int shift = ix.key_bits - kCellBits;
+    const int ox = (int) (quant_axis(qx, qp.lx, qp.scale, qp.qmax) >> shift), oy = (int) (quant_axis(qy, qp.ly, qp.scale, qp.qmax) >> shift),
+              oz = (int) (quant_axis(qz, qp.lz, qp.scale, qp.qmax) >> shift);
+    const int own = ox | (oy << kCellBits) | (oz << (2 * kCellBits));
     float2 slots[kStackDepth];
     float2 top = make_float2(INFINITY, __int_as_float(kLinkDone));
     int sp = 0;
     unsigned long long best_key = nn_key(best, (unsigned) best_idx);
     int link = kLinkPop;
-    const float r = sqrtf(best) * 1.00001f + fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) * 1e-6f + 1e-30f;
-    const int shift = ix.key_bits - kCellBits;
+    auto enter = [&](int cell) {
+        const int l = __ldg(ix.cells + cell);
+        if (l == kCellEmpty) return;
+        if (l < 0) {  // a single point
+            const float4 p = __ldg(ix.pts + ~l);
+            const unsigned long long k = nn_key(l2_simple(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
+            if (k < best_key) {
+                best_key = k;
+                best_pos = ~l;
+            }
+            return;
+        }
+        if (link >= 0) {
+            slots[sp++] = top;
+            top = make_float2(0.0f, __int_as_float(link));  // bound 0: always admitted; its node step prunes
+        }
+        link = l;
+    };
+    bool own_done = false;
+    if (best_pos < 0) {  // no candidate: the own cell first, on its own
+        enter(own);
+        walk(qx, qy, qz, ix.nodes, link, slots, top, sp, best_key, best_pos);
+        own_done = true;
+        link = kLinkPop;
+        top = make_float2(INFINITY, __int_as_float(kLinkDone));
+        sp = 0;
+    }
+    const float bound = key_bound(best_key);
+    const float r = sqrtf(bound) * 1.00001f + fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) * 1e-6f + 1e-30f;
     const int ax = (int) (quant_axis(qx - r, qp.lx, qp.scale, qp.qmax) >> shift), bx = (int) (quant_axis(qx + r, qp.lx, qp.scale, qp.qmax) >> shift);
     const int ay = (int) (quant_axis(qy - r, qp.ly, qp.scale, qp.qmax) >> shift), by = (int) (quant_axis(qy + r, qp.ly, qp.scale, qp.qmax) >> shift);
     const int az = (int) (quant_axis(qz - r, qp.lz, qp.scale, qp.qmax) >> shift), bz = (int) (quant_axis(qz + r, qp.lz, qp.scale, qp.qmax) >> shift);
     if (best_pos < 0 || bx - ax > 1 || by - ay > 1 || bz - az > 1) {
-        if (aabb_dist(qx, qy, qz, rlo, rhi) <= best) link = root_link;
+        if (aabb_dist(qx, qy, qz, rlo, rhi) <= bound) link = root_link;
     } else {
-        // the query's own cell goes last = ends up as the first link (or on top of the stack)
-        const int ox = (int) (quant_axis(qx, qp.lx, qp.scale, qp.qmax) >> shift), oy = (int) (quant_axis(qy, qp.ly, qp.scale, qp.qmax) >> shift),
-                  oz = (int) (quant_axis(qz, qp.lz, qp.scale, qp.qmax) >> shift);
-        const int own = ox | (oy << kCellBits) | (oz << (2 * kCellBits));
-        auto enter = [&](int cell) {
-            const int l = __ldg(ix.cells + cell);
-            if (l == kCellEmpty) return;
-            if (l < 0) {  // a single point
-                const float4 p = __ldg(ix.pts + ~l);
-                const unsigned long long k = nn_key(l2_simple(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
-                if (k < best_key) {
-                    best_key = k;
-                    best_pos = ~l;
-                }
-                return;
-            }
-            if (link >= 0) {
-                slots[sp++] = top;
-                top = make_float2(0.0f, __int_as_float(link));  // bound 0: always admitted; its node step prunes
-            }
-            link = l;
-        };
         for (int cz = az; cz <= bz; ++cz)
             for (int cy = ay; cy <= by; ++cy)
                 for (int cx = ax; cx <= bx; ++cx) {
                     const int cell = cx | (cy << kCellBits) | (cz << (2 * kCellBits));
                     if (cell != own) enter(cell);
                 }
-        enter(own);
+        if (!own_done) enter(own);  // last = first link to walk
     }
     walk(qx, qy, qz, ix.nodes, link, slots, top, sp, best_key, best_pos);
     best = key_bound(best_key);
