@@ -520,6 +520,11 @@ __device__ __forceinline__ void nn_search_cells(float qx, float qy, float qz, co
     best = key_bound(best_key);
     best_idx = (int) (unsigned) best_key;
 }
+#else
+__device__ __forceinline__ void nn_search_cells(float qx, float qy, float qz, const NnIndex &ix, float &best,
+                                                int &best_idx, int &best_pos) {
+    nn_search(qx, qy, qz, ix, best, best_idx, best_pos);  // tuning builds with multi-point leaves: no entry table
+}
 #endif
 
 }  // namespace wavecu

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) lumold_corr_kerne
             best_pos = warm;
         }
     }
-    nn_search(x, y, z, a.ix, best, best_idx, best_pos);
+    nn_search_cells(x, y, z, a.ix, best, best_idx, best_pos);
     a.pos_out[s] = best_pos;
 }
 

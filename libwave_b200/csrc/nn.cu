@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kNnThreads) nn_kernel(const float4 *__restrict
     if (orig == 0x7fffffff) return;  // pad (non-finite query): left at -1 / inf by the caller's fill
     float best = thr;
     int best_idx = 0x7fffffff, best_pos = -1;
-    nn_search(q.x, q.y, q.z, ix, best, best_idx, best_pos);
+    nn_search_cells(q.x, q.y, q.z, ix, best, best_idx, best_pos);
     out_idx[orig] = best_pos >= 0 ? best_idx : -1;
     out_d2[orig] = best_pos >= 0 ? best : INFINITY;
 }
