@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
     // iteration); then thread 0 runs the estimator
     __shared__ unsigned long long s_lo[NV + 1];
     __shared__ long long s_hi[NV + 1];
+    __shared__ double s_val[NV + 1];
     if (threadIdx.x <= NV) {
         __int128 t = 0;
 #pragma unroll 4
@@ -365,12 +366,18 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
         }
         s_lo[threadIdx.x] = (unsigned long long) t;
         s_hi[threadIdx.x] = (long long) (t >> 64);
+        // each thread also converts its own sum (the fixed-point exponent depends only on the slot)
+        const int i = threadIdx.x;
+        int k;
+        if (EST == WAVECU_EST_SVD) k = (i < 6) ? a.mc->k_lin : (i < 15 ? a.mc->k_quad : a.mc->k_d2);
+        else k = (i == 27) ? a.mc->k_d2 : a.mc->k_quad - 3;
+        s_val[i] = acc_to_double((unsigned long long) t, (long long) (t >> 64), k);
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
     IcpState &st = *a.st;
     const MatchConsts &mc = *a.mc;
-    auto val = [&](int i, int k) { return acc_to_double(s_lo[i], s_hi[i], k); };
+    auto val = [&](int i, int /*k*/) { return s_val[i]; };
     const long long n = (long long) s_lo[NV];
     if (n < 3) {  // min_number_correspondences_
         st.n_corr = (int) n;
