@@ -15,7 +15,7 @@ struct wavecu_gicp;
 namespace wave {
 
 struct GICPMatcherParams {
-    explicit GICPMatcherParams(const std::string &config_path);
+    GICPMatcherParams(const std::string &config_path);  // implicit, as gicp.hpp:31
     GICPMatcherParams() {}
 
     int corr_rand = 10;     ///< neighbours used for each point's covariance

@@ -17,7 +17,7 @@ struct wavecu_icp;
 namespace wave {
 
 struct ICPMatcherParams {
-    explicit ICPMatcherParams(const std::string &config_path);
+    ICPMatcherParams(const std::string &config_path);  // implicit, as icp.hpp:31
     ICPMatcherParams() {}
 
     double max_corr = 3;               ///< correspondences farther apart than this are dropped

@@ -40,10 +40,18 @@ void MultiMatcher<T, R>::spin(int threadid) {
             this->input.pop();
         }
         this->ip_condition.notify_all();  // a slot of the bounded queue is free again
-        matcher.setRef(std::get<1>(job));
-        matcher.setTarget(std::get<2>(job));
-        matcher.match();
-        matcher.estimateInfo();
+        // the reference's workers never throw (PCL reports failure through hasConverged()); here a
+        // device error surfaces as std::runtime_error from the matcher - the job then yields the
+        // matcher's previous result/identity instead of ending the process through std::terminate,
+        // and remaining_matches still decrements
+        try {
+            matcher.setRef(std::get<1>(job));
+            matcher.setTarget(std::get<2>(job));
+            matcher.match();
+            matcher.estimateInfo();
+        } catch (const std::exception &e) {
+            LOG_ERROR("MultiMatcher worker %d: job %d failed: %s", threadid, std::get<0>(job), e.what());
+        }
         {
             std::unique_lock<std::mutex> lockop(this->op_mutex);
             this->output.emplace(std::get<0>(job), matcher.getResult(), matcher.getInfo());

@@ -15,7 +15,7 @@ class Matcher {
     EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 
     /// res: edge length of the voxel filter applied before matching (<= 0: full resolution)
-    explicit Matcher(float res) : resolution(res) {}
+    Matcher(float res) : resolution(res) {}  // implicit, as matcher.hpp:32
     Matcher() : resolution(-1) {}
     virtual ~Matcher() {}
 

@@ -5,13 +5,15 @@
 // (multi_matcher.hpp:73) - pops the oldest finished result as its doc comment describes.
 //
 // On the B200 a worker is a host thread driving its own C-ABI handle, i.e. its own CUDA stream and
-// device buffers: matches of different workers overlap on the GPU.  Workers are spread round-robin
-// over the visible devices, so on the 8-GPU box the same class shards a batch of scans across all
-// GPUs with no data-path communication.
+// device buffers: matches of different workers overlap on the GPU.  With WAVE_MATCHING_DEVICE=all the
+// workers' matchers (ICP, GICP and NDT alike) are spread round-robin over the visible devices, so on
+// the 8-GPU box the same class shards a batch of scans across all GPUs with no data-path
+// communication; unset, every matcher sits on device 0.
 #ifndef WAVE_MATCHING_MULTI_MATCHER_HPP
 #define WAVE_MATCHING_MULTI_MATCHER_HPP
 
 #include <condition_variable>
+#include <exception>
 #include <mutex>
 #include <queue>
 #include <thread>
@@ -20,6 +22,7 @@
 
 #include "wave/matching/matcher.hpp"
 #include "wave/matching/pcl_common.hpp"
+#include "wave/utils/log.hpp"
 
 namespace wave {
 

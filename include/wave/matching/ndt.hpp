@@ -15,7 +15,7 @@ namespace wave {
 
 struct NDTMatcherParams {
     NDTMatcherParams() {}
-    explicit NDTMatcherParams(const std::string &config_path);
+    NDTMatcherParams(const std::string &config_path);  // implicit, as ndt.hpp:35
 
     int step_size = 3;            ///< maximum Newton line-search step (an int in the reference too)
     int max_iter = 100;           ///< cap on iterations

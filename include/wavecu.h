@@ -159,7 +159,14 @@ typedef struct {
     int max_iter;    /* ndt.hpp:38, default 100 */
     double t_eps;    /* ndt.hpp:39, default 1e-8 */
     float res;       /* ndt.hpp:40, default 5 */
+    /* Not a reference field: which PCL release's computeStepLengthMT the match follows.  PCL 1.8
+     * initialises `interval_converged = (step_max - step_min) > 0`, which skips the More-Thuente
+     * search whenever step_size > t_eps / 2 (always for the reference's values) and leaves a capped
+     * Newton step; PCL >= 1.9 tests `< 0` and searches.  Only the latter passes the reference's own
+     * smallDisplacement test (tests/ndt_tests.cpp:85-102), so it is the default. */
+    int line_search; /* WAVECU_NDT_LS_*, default WAVECU_NDT_LS_MORE_THUENTE */
 } wavecu_ndt_params;
+enum { WAVECU_NDT_LS_PCL18 = 0, WAVECU_NDT_LS_MORE_THUENTE = 1 };
 
 void wavecu_ndt_default_params(wavecu_ndt_params *p);
 
@@ -182,6 +189,7 @@ int wavecu_ndt_grid(wavecu_ndt *h, int *n_cells, int *voxel, int *count, float *
  * fp32 matrix T16: score, gradient (6) and Hessian (6x6, row major). */
 int wavecu_ndt_derivatives(wavecu_ndt *h, const double pose6[6], const float T16[16], double *score, double g6[6],
                            double H36[36]);
+/* n_cells: the normal-distribution cells (>= 6 points, usable covariance) - what wavecu_ndt_grid lists */
 int wavecu_ndt_stats(wavecu_ndt *h, long long *kernel_launches, long long *derivative_passes, int *n_cells);
 
 /* ---- GICPMatcher (include/wave/matching/gicp.hpp:30-65, src/gicp.cpp:20-64) -------------------------

@@ -27,8 +27,9 @@ class IcpParamsC(C.Structure):
 
 
 class NdtParamsC(C.Structure):
-    """wavecu_ndt_params == wave::NDTMatcherParams (ndt.hpp:37-41)."""
-    _fields_ = [("step_size", C.c_int), ("max_iter", C.c_int), ("t_eps", C.c_double), ("res", C.c_float)]
+    """wavecu_ndt_params == wave::NDTMatcherParams (ndt.hpp:37-41) + the PCL line-search switch."""
+    _fields_ = [("step_size", C.c_int), ("max_iter", C.c_int), ("t_eps", C.c_double), ("res", C.c_float),
+                ("line_search", C.c_int)]
 
 
 class GicpParamsC(C.Structure):

@@ -106,8 +106,18 @@ __device__ __forceinline__ void atomic_add128(Acc128 *acc, unsigned long long x_
     if (add_hi != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc->hi), (unsigned long long) add_hi);
 }
 
-__device__ __forceinline__ double acc_to_double(unsigned long long lo, long long hi, int k) {
-    return ldexp(__ll2double_rn(hi), 64 - k) + ldexp(__ull2double_rn(lo), -k);
+// 128-bit fixed point -> fp64, sign-magnitude: |v| = hi * 2^64 + lo is converted (each half rounds
+// once, the sum once more) and the sign re-applied.  Converting a negative total's two's-complement
+// halves directly would round lo ~ 2^64 - |v| to 53 bits before the cancelling add and lose the
+// low bits of small negative sums.  Same formula in oracle/smallmat.hpp and the host code.
+__host__ __device__ __forceinline__ double acc_to_double(unsigned long long lo, long long hi, int k) {
+    const bool neg = hi < 0;
+    if (neg) {  // two's-complement negate of the 128-bit value
+        lo = ~lo + 1ull;
+        hi = ~hi + (lo == 0ull ? 1 : 0);
+    }
+    const double mag = ldexp((double) hi, 64 - k) + ldexp((double) lo, -k);
+    return neg ? -mag : mag;
 }
 
 }  // namespace wavecu

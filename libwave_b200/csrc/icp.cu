@@ -734,9 +734,7 @@ int IcpHandle::read_acc(int n_values, __int128 *out) {
 namespace {
 
 double fix_to_double(__int128 v, int k) {
-    const long long hi = (long long) (v >> 64);
-    const unsigned long long lo = (unsigned long long) v;
-    return std::ldexp((double) hi, 64 - k) + std::ldexp((double) lo, -k);
+    return acc_to_double((unsigned long long) v, (long long) (v >> 64), k);  // sign-magnitude, common.cuh
 }
 
 // N x N solve by Gaussian elimination with partial pivoting (fixed order), used column by column

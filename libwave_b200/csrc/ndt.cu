@@ -166,9 +166,12 @@ __device__ __forceinline__ unsigned hash_voxel(int v, unsigned mask) {
 }
 
 __global__ void ndt_hash_insert_kernel(const NdtLeafDev *__restrict__ leaves, int n_leaves, int *table_key,
-                                       int *table_slot, unsigned mask) {
+                                       int *table_slot, unsigned mask, int *n_valid) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_leaves || !leaves[i].valid) return;
+    const bool valid = i < n_leaves && leaves[i].valid;
+    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_valid, __popc(ballot));
+    if (!valid) return;
     const int v = leaves[i].voxel;
     unsigned h = hash_voxel(v, mask);
     for (;;) {
@@ -538,7 +541,9 @@ struct NdtHandle {
     VoxelWork vox;
     NdtLeafDev *d_leaves = nullptr;
     size_t leaf_cap = 0;
-    int n_leaves = 0;
+    int n_leaves = 0;      // occupied voxels
+    int n_cells = -1;      // of which normal-distribution cells (>= 6 points, usable covariance); -1: not read yet
+    int *d_n_valid = nullptr;
     int *d_table_key = nullptr, *d_table_slot = nullptr;
     size_t table_cap = 0;
     unsigned table_mask = 0;
@@ -568,6 +573,7 @@ struct NdtHandle {
         WCU_CHECK(cudaHostAlloc((void **) &h_seq, sizeof(int), cudaHostAllocMapped));
         *h_seq = 0;
         WCU_CHECK(cudaMalloc((void **) &d_ticket, sizeof(unsigned)));
+        WCU_CHECK(cudaMalloc((void **) &d_n_valid, sizeof(int)));
         WCU_CHECK(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), stream));
         return WAVECU_OK;
     }
@@ -593,6 +599,7 @@ struct NdtHandle {
         resolution = clamped_res();
         grid_ok = false;
         n_leaves = 0;
+        n_cells = 0;
         grid_dirty = false;
         if (n_tgt == 0) return WAVECU_OK;
         int status = 0;
@@ -621,9 +628,11 @@ struct NdtHandle {
         WCU_CHECK(cudaMemsetAsync(d_table_key, 0xff, slots * sizeof(int), stream));
         ndt_leaf_kernel<<<(unsigned) ((n_tgt + 255) / 256), 256, 0, stream>>>(d_tgt, vox.d_keys, vox.d_vals, vox.d_pos,
                                                                               n_tgt, d_leaves);
+        WCU_CHECK(cudaMemsetAsync(d_n_valid, 0, sizeof(int), stream));
+        n_cells = -1;
         if (n_leaves)
             ndt_hash_insert_kernel<<<(n_leaves + 255) / 256, 256, 0, stream>>>(d_leaves, n_leaves, d_table_key,
-                                                                               d_table_slot, table_mask);
+                                                                               d_table_slot, table_mask, d_n_valid);
         launches += 2;
         WCU_CHECK(cudaGetLastError());
         grid_ok = true;
@@ -728,8 +737,11 @@ struct NdtHandle {
                     double a_l = 0, a_u = 0;
                     double f_l = psi_mt(a_l, phi_0, phi_0, d_phi_0, mu), g_l = dpsi_mt(d_phi_0, d_phi_0, mu);
                     double f_u = psi_mt(a_u, phi_0, phi_0, d_phi_0, mu), g_u = dpsi_mt(d_phi_0, d_phi_0, mu);
-                    // PCL 1.8: true whenever step_max > step_min, which skips the loop below
-                    bool interval_converged = (step_max - step_min) > 0, open_interval = true;
+                    // PCL 1.8: `> 0`, true whenever step_max > step_min, which skips the loop below;
+                    // PCL >= 1.9: `< 0`, the search runs (wavecu.h, wavecu_ndt_params::line_search)
+                    bool interval_converged = prm.line_search == WAVECU_NDT_LS_PCL18 ? (step_max - step_min) > 0
+                                                                                      : (step_max - step_min) < 0,
+                         open_interval = true;
                     a_t = std::max(std::min(delta_p_norm, step_max), step_min);
                     double x_t[6];
                     auto evaluate = [&](bool hess) -> int {
@@ -798,6 +810,7 @@ struct NdtHandle {
         if (h_sums) cudaFreeHost(h_sums);
         if (h_seq) cudaFreeHost(h_seq);
         if (d_ticket) cudaFree(d_ticket);
+        if (d_n_valid) cudaFree(d_n_valid);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -818,6 +831,7 @@ void wavecu_ndt_default_params(wavecu_ndt_params *p) {
     p->max_iter = 100;
     p->t_eps = 1e-8;
     p->res = 5.f;
+    p->line_search = WAVECU_NDT_LS_MORE_THUENTE;
 }
 
 int wavecu_ndt_create(const wavecu_ndt_params *params, int device, void *stream, wavecu_ndt **out) {
@@ -940,7 +954,15 @@ int wavecu_ndt_stats(wavecu_ndt *w, long long *kernel_launches, long long *deriv
     if (!w) return WAVECU_ERR_ARG;
     if (kernel_launches) *kernel_launches = w->h.launches + w->h.vox.launches;
     if (derivative_passes) *derivative_passes = w->h.derivative_passes;
-    if (n_cells) *n_cells = w->h.n_leaves;
+    if (n_cells) {
+        NdtHandle &h = w->h;
+        if (h.n_cells < 0) {  // counted by the hash-insert kernel of the last grid build
+            WCU_CHECK(cudaSetDevice(h.device));
+            WCU_CHECK(cudaMemcpyAsync(&h.n_cells, h.d_n_valid, sizeof(int), cudaMemcpyDeviceToHost, h.stream));
+            WCU_CHECK(cudaStreamSynchronize(h.stream));
+        }
+        *n_cells = h.n_cells;
+    }
     return WAVECU_OK;
 }
 

@@ -4,7 +4,6 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
-#include <mutex>
 #include <vector>
 
 #include "../../include/wavecu.h"
@@ -13,12 +12,12 @@
 namespace wavecu {
 
 namespace {
-std::mutex g_err_mutex;
-std::string g_last_error;
+// per host thread: MultiMatcher workers each drive their own handle, and a failure in one of them
+// must not be reported with (or overwritten by) another thread's message
+thread_local std::string g_last_error;
 }  // namespace
 
 void set_last_error(const std::string &msg) {
-    std::lock_guard<std::mutex> lock(g_err_mutex);
     g_last_error = msg;
 }
 
@@ -123,10 +122,7 @@ struct wavecu_nn {
 extern "C" {
 
 const char *wavecu_last_error(void) {
-    static thread_local std::string copy;
-    std::lock_guard<std::mutex> lock(g_err_mutex);
-    copy = g_last_error;
-    return copy.c_str();
+    return g_last_error.c_str();  // the calling thread's own last message
 }
 
 int wavecu_device_count(void) {

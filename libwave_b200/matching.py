@@ -307,9 +307,15 @@ class NDTMatcherParams:
     t_eps: float = 1e-8
     res: float = 5.0
     min_res: float = 0.05
+    # not a reference field (wavecu.h): NDT_LS_MORE_THUENTE = PCL >= 1.9's computeStepLengthMT,
+    # NDT_LS_PCL18 = PCL 1.8's, whose More-Thuente search never runs
+    line_search: int = 1
 
     def to_c(self) -> capi.NdtParamsC:
-        return capi.NdtParamsC(int(self.step_size), self.max_iter, self.t_eps, self.res)
+        return capi.NdtParamsC(int(self.step_size), self.max_iter, self.t_eps, self.res, int(self.line_search))
+
+
+NDT_LS_PCL18, NDT_LS_MORE_THUENTE = 0, 1
 
 
 class NDTMatcher(Matcher):

@@ -127,6 +127,12 @@ void wo_fix_scales(const float *src, size_t n_src, const float *tgt, size_t n_tg
 }
 
 void wo_rotation_from_sigma(const double *S9, double *R9) { rotation_from_sigma(S9, R9); }
+// sum of llrint(terms[i] * 2^k) in 128-bit fixed point, converted back (Fix128::value)
+double wo_fix128_sum(const double *terms, size_t n, int k) {
+    Fix128 f;
+    for (size_t i = 0; i < n; ++i) f.add(terms[i], k);
+    return f.value(k);
+}
 int wo_solve6(const double *A36, const double *b6, double *x6) { return solve_pp<6>(A36, b6, x6) ? 1 : 0; }
 
 }  // extern "C"
@@ -212,6 +218,7 @@ struct wo_ndt_params_c {
     int max_iter;
     double t_eps;
     float res;
+    int line_search;
 };
 
 // out: T16 (fp32 final transform), pose6, converged, iterations, n_voxels, score; trace arrays need
@@ -224,6 +231,7 @@ void wo_ndt_align(const float *src, size_t n_src, const float *tgt, size_t n_tgt
     prm.max_iter = p->max_iter;
     prm.t_eps = p->t_eps;
     prm.res = p->res;
+    prm.line_search = p->line_search;
     NdtResult r;
     ndt_align(src, n_src, tgt, n_tgt, prm, r);
     std::memcpy(T16, r.final_T, sizeof r.final_T);

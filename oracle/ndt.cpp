@@ -7,11 +7,15 @@
 // Magnusson 2009 eq. 6.8-6.21; More & Thuente 1994).  PCL is not vendored: PARITY UNPINNED at the bit
 // level; the reference's own tests (tests/ndt_tests.cpp, Frobenius < 0.12) are re-stated in tests/.
 //
-// Restated faithfully, including two PCL 1.8 quirks that shape the result:
-//   * computeStepLengthMT initialises `interval_converged = (step_max - step_min) > 0`, so with
-//     step_max > step_min (always, for libwave's step_size = 3, t_eps = 1e-8) the More-Thuente loop
-//     never runs and the step is simply clamp(|delta_p|, step_min, step_max) along the Newton
-//     direction; the loop is restated anyway for the degenerate step_max <= step_min case.
+// Restated faithfully, including two PCL quirks that shape the result:
+//   * PCL 1.8's computeStepLengthMT initialises `interval_converged = (step_max - step_min) > 0`, so
+//     with step_max > step_min (always, for libwave's step_size = 3, t_eps = 1e-8) the More-Thuente
+//     loop never runs and the step is simply clamp(|delta_p|, step_min, step_max) along the Newton
+//     direction (NdtParams::line_search = 0).  PCL >= 1.9 corrected the test to `< 0` and the
+//     search runs (line_search = 1, the default here): only that behaviour passes the reference's
+//     own smallDisplacement case (tests/ndt_tests.cpp:85-102, res 0.3, 0.2 m, bound 0.12) - with the
+//     1.8 line the capped Newton steps on the indefinite Hessians of that case wander metres away
+//     (tests/test_oracle_ndt.py records both).
 //   * updateDerivatives drops a neighbour whose d2 * exp(...) falls outside [0, 1] *after* its
 //     score increment was formed (the increment is discarded with it).
 // Deviations (documented): voxels whose covariance has a negative eigenvalue are dropped instead of
@@ -507,7 +511,10 @@ void ndt_align(const float *source, size_t n_src, const float *target, size_t n_
                 double a_l = 0, a_u = 0;
                 double f_l = psi_mt(a_l, phi_0, phi_0, d_phi_0, mu), g_l = dpsi_mt(d_phi_0, d_phi_0, mu);
                 double f_u = psi_mt(a_u, phi_0, phi_0, d_phi_0, mu), g_u = dpsi_mt(d_phi_0, d_phi_0, mu);
-                bool interval_converged = (step_max - step_min) > 0, open_interval = true;  // sic (PCL 1.8)
+                // PCL 1.8: `(step_max - step_min) > 0` (sic) - true whenever step_max > step_min, which skips
+                // the loop below; PCL >= 1.9: `< 0`, the More-Thuente search runs
+                bool interval_converged = prm.line_search ? (step_max - step_min) < 0 : (step_max - step_min) > 0,
+                     open_interval = true;
                 a_t = std::max(std::min(step_init, step_max), step_min);
                 double x_t[6];
                 auto evaluate = [&](bool hess) {

@@ -12,6 +12,7 @@ struct NdtParams {  // wave::NDTMatcherParams, ndt.hpp:37-41
     int max_iter = 100;
     double t_eps = 1e-8;
     float res = 5;
+    int line_search = 1;  // 1: More-Thuente search runs (PCL >= 1.9); 0: PCL 1.8's skipped search
 };
 
 struct NdtLeaf {

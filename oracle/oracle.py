@@ -172,6 +172,15 @@ def fix_scales(source, target, max_corr):
     return tuple(int(v) for v in k)
 
 
+def fix128_sum(terms, k: int) -> float:
+    """Exact 128-bit fixed-point sum of round(terms * 2^k), converted back to fp64 (smallmat.hpp)."""
+    t = np.ascontiguousarray(terms, dtype=np.float64)
+    L = lib()
+    L.wo_fix128_sum.restype = C.c_double
+    L.wo_fix128_sum.argtypes = [_dp, C.c_size_t, C.c_int]
+    return float(L.wo_fix128_sum(_d(t), t.shape[0], k))
+
+
 def rotation_from_sigma(S):
     S = np.ascontiguousarray(S, dtype=np.float64).reshape(9)
     R = np.empty(9, dtype=np.float64)
@@ -320,20 +329,26 @@ def estimate_censi(ref, target, corr_q, corr_m, T, lin_covar=2.5e-4, ang_covar=7
 
 # ---- NDT (oracle/ndt.cpp) -------------------------------------------------------------------------
 class NdtParamsC(C.Structure):
-    _fields_ = [("step_size", C.c_int), ("max_iter", C.c_int), ("t_eps", C.c_double), ("res", C.c_float)]
+    _fields_ = [("step_size", C.c_int), ("max_iter", C.c_int), ("t_eps", C.c_double), ("res", C.c_float),
+                ("line_search", C.c_int)]
 
 
 class NdtResult:
     pass
 
 
-def ndt_align(source, target, *, step_size=3, max_iter=100, t_eps=1e-8, res=5.0) -> NdtResult:
-    """pcl::NormalDistributionsTransform::align as NDTMatcher drives it (src/ndt.cpp:18-65)."""
+NDT_LS_PCL18, NDT_LS_MORE_THUENTE = 0, 1
+
+
+def ndt_align(source, target, *, step_size=3, max_iter=100, t_eps=1e-8, res=5.0,
+              line_search=NDT_LS_MORE_THUENTE) -> NdtResult:
+    """pcl::NormalDistributionsTransform::align as NDTMatcher drives it (src/ndt.cpp:18-65).
+    line_search: NDT_LS_MORE_THUENTE (PCL >= 1.9) or NDT_LS_PCL18 (the search PCL 1.8 skips)."""
     s, t = xyzw(source), xyzw(target)
     L = lib()
     L.wo_ndt_align.argtypes = [_fp, C.c_size_t, _fp, C.c_size_t, C.POINTER(NdtParamsC), _fp, _dp, _ip, _ip, _ip, _dp,
                                _dp, _ip]
-    prm = NdtParamsC(step_size, max_iter, t_eps, res)
+    prm = NdtParamsC(step_size, max_iter, t_eps, res, line_search)
     T = np.empty(16, dtype=np.float32)
     pose = np.empty(6, dtype=np.float64)
     conv, iters, nv, ntr = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -11,14 +11,17 @@ namespace wo {
 
 // ---- order-independent accumulation: 128-bit fixed point ------------------------------------
 // term -> llrint(term * 2^k) (round-to-nearest-even), summed exactly in a signed 128-bit integer,
-// converted back as ldexp((double)hi, 64 - k) + ldexp((double)lo, -k).
+// converted back sign-magnitude: |v| = hi * 2^64 + lo as ldexp((double)hi, 64 - k) + ldexp((double)lo, -k),
+// then the sign (the two's-complement halves of a negative total would lose its low bits).
 struct Fix128 {
     __int128 v = 0;
     inline void add(double term, int k) { v += (__int128) std::llrint(std::ldexp(term, k)); }
     inline double value(int k) const {
-        const int64_t hi = (int64_t)(v >> 64);
-        const uint64_t lo = (uint64_t) v;
-        return std::ldexp((double) hi, 64 - k) + std::ldexp((double) lo, -k);
+        const bool neg = v < 0;
+        const unsigned __int128 m = neg ? (unsigned __int128) 0 - (unsigned __int128) v : (unsigned __int128) v;
+        const uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t) m;
+        const double mag = std::ldexp((double) hi, 64 - k) + std::ldexp((double) lo, -k);
+        return neg ? -mag : mag;
     }
 };
 

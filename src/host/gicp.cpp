@@ -16,6 +16,8 @@
 
 namespace wave {
 
+int pick_matcher_device();  // src/host/icp.cpp
+
 namespace {
 [[noreturn]] void fail(const char *what) { throw std::runtime_error(std::string(what) + ": " + wavecu_last_error()); }
 }  // namespace
@@ -41,8 +43,7 @@ GICPMatcher::GICPMatcher(GICPMatcherParams params1) : params(params1) {
     c.r_eps = this->params.r_eps;
     c.fit_eps = this->params.fit_eps;
     c.res = this->resolution;
-    const char *env = std::getenv("WAVE_MATCHING_DEVICE");
-    const int device = (env && std::string(env) != "all") ? std::atoi(env) : 0;
+    const int device = pick_matcher_device();  // WAVE_MATCHING_DEVICE, shared by the three matchers (icp.cpp)
     if (wavecu_gicp_create(&c, device, nullptr, &this->handle) != WAVECU_OK) fail("wavecu_gicp_create");
 }
 

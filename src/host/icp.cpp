@@ -38,9 +38,12 @@ wavecu_icp_params to_c(const ICPMatcherParams &p) {
     return c;
 }
 
+}  // namespace
+
 // WAVE_MATCHING_DEVICE=<n> pins every matcher to device n; WAVE_MATCHING_DEVICE=all spreads
-// successive matchers round-robin over the visible devices (MultiMatcher on the 8-GPU box).
-int pick_device() {
+// successive matchers (of all three kinds) round-robin over the visible devices - MultiMatcher on
+// the 8-GPU box; unset: device 0.
+int pick_matcher_device() {
     static std::atomic<int> next{0};
     const char *env = std::getenv("WAVE_MATCHING_DEVICE");
     if (!env) return 0;
@@ -50,8 +53,6 @@ int pick_device() {
     }
     return std::atoi(env);
 }
-
-}  // namespace
 
 ICPMatcherParams::ICPMatcherParams(const std::string &config_path) {
     ConfigParser parser;
@@ -78,7 +79,7 @@ ICPMatcherParams::ICPMatcherParams(const std::string &config_path) {
 ICPMatcher::ICPMatcher(ICPMatcherParams params1) : params(params1) {
     this->resolution = this->params.res;
     const wavecu_icp_params c = to_c(this->params);
-    if (wavecu_icp_create(&c, pick_device(), nullptr, &this->handle) != WAVECU_OK) fail("wavecu_icp_create");
+    if (wavecu_icp_create(&c, pick_matcher_device(), nullptr, &this->handle) != WAVECU_OK) fail("wavecu_icp_create");
 }
 
 ICPMatcher::ICPMatcher(ICPMatcher &&other) noexcept

@@ -13,6 +13,8 @@
 
 namespace wave {
 
+int pick_matcher_device();  // src/host/icp.cpp
+
 namespace {
 [[noreturn]] void fail(const char *what) { throw std::runtime_error(std::string(what) + ": " + wavecu_last_error()); }
 
@@ -22,6 +24,10 @@ wavecu_ndt_params to_c(const NDTMatcherParams &p) {
     c.max_iter = p.max_iter;
     c.t_eps = p.t_eps;
     c.res = p.res;
+    // the reference's params carry no such field: PCL >= 1.9's line search unless the caller asks for
+    // PCL 1.8's skipped one (wavecu.h)
+    const char *ls = std::getenv("WAVE_MATCHING_NDT_PCL18");
+    c.line_search = (ls && *ls && *ls != '0') ? WAVECU_NDT_LS_PCL18 : WAVECU_NDT_LS_MORE_THUENTE;
     return c;
 }
 }  // namespace
@@ -48,8 +54,7 @@ NDTMatcher::NDTMatcher(NDTMatcherParams params1) {
     }
     this->resolution = this->params.res;
     const wavecu_ndt_params c = to_c(this->params);
-    const char *env = std::getenv("WAVE_MATCHING_DEVICE");
-    const int device = (env && std::string(env) != "all") ? std::atoi(env) : 0;
+    const int device = pick_matcher_device();  // WAVE_MATCHING_DEVICE, shared by the three matchers (icp.cpp)
     if (wavecu_ndt_create(&c, device, nullptr, &this->handle) != WAVECU_OK) fail("wavecu_ndt_create");
 }
 

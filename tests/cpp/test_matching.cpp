@@ -169,13 +169,17 @@ int main(int argc, char **argv) {
         EXPECT(got == 8 && all, "simultaneousmatching");
         std::printf("%-18s results=%d\n", "multimatcher", got);
     }
-    if (argc >= 4) {  // NDTTests (tests/ndt_tests.cpp): initialization, fullResNullMatch, nullDisplacement
+    if (argc >= 4) {  // NDTTests (tests/ndt_tests.cpp): initialization, fullResNullMatch, nullDisplacement,
+                      // smallDisplacement
         const std::string ndt_config = argv[3];
         const float ndt_threshold = 0.12f;  // tests/ndt_tests.cpp:37
         { NDTMatcher matcher{NDTMatcherParams()}; }
-        const float res_cases[] = {-1.f /* keep the yaml's 0.05 */, 0.1f};
-        for (float r : res_cases) {
+        struct NCase { float res; double tx; };
+        const NCase ncases[] = {{-1.f /* keep the yaml's 0.05 */, 0.0}, {0.1f, 0.0}, {0.3f, 0.2}};
+        for (const NCase &nc : ncases) {
+            const float r = nc.res;
             Affine3 perturb = Affine3::Identity();
+            perturb.translation() << nc.tx, 0, 0;
             NDTMatcherParams params(ndt_config);
             if (r > 0) params.res = r;
             NDTMatcher matcher(params);
@@ -183,9 +187,10 @@ int main(int argc, char **argv) {
             matcher.setup(ref, target);
             const bool match_success = matcher.match();
             const double diff = (matcher.getResult().matrix() - perturb.matrix()).norm();
-            EXPECT(match_success, "ndt_null");
-            EXPECT(diff < ndt_threshold, "ndt_null");
-            std::printf("%-18s res=%.2f match=%d diff=%.3e\n", "ndt_null", matcher.getRes(), (int) match_success, diff);
+            const char *name = nc.tx == 0.0 ? "ndt_null" : "ndt_smallDisp";
+            EXPECT(match_success, name);
+            EXPECT(diff < ndt_threshold, name);
+            std::printf("%-18s res=%.2f match=%d diff=%.3e\n", name, matcher.getRes(), (int) match_success, diff);
         }
     }
     if (argc >= 5) {  // GICPTests (tests/gicp_tests.cpp): fullResNullMatch, nullDisplacement, smallDisplacement

@@ -1,5 +1,5 @@
-"""GPU tests at BASELINE.json's full sizes, through size-independent properties (the oracle would
-need minutes per case at these sizes):
+"""GPU tests at BASELINE.json's full sizes: the ICP configurations against the oracle itself (with
+all host threads its exact NN search takes seconds at 1 M points), and size-independent properties:
   * a rigidly moved copy of a cloud (the premise of every reference test) must be recovered, and at
     convergence every source point must correspond to its own copy - an index-exact property;
   * nearest neighbours of a cloud in itself are the identity permutation with zero distance;
@@ -84,6 +84,84 @@ def test_point_to_plane_1m_converges_to_truth(W, synth):
     assert np.abs(T[:3, 3] - synth.T_TRUE[:3, 3]).max() < 2e-2
     assert rot_angle(T[:3, :3], synth.T_TRUE[:3, :3]) < 2e-3
     assert m.iterations <= 10
+
+
+def _host_threads():
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def test_bench_workload_1m_point_to_plane_equals_oracle(W, oracle, synth):
+    """BASELINE config 2 at its own size - the exact workload bench.py times: iteration count, MSE
+    trace, correspondence counts, every correspondence index and fp32 distance equal to the oracle's
+    (integer / fp32 work: bit-exact); transforms within one fp32 ulp of the oracle's exact-sum mode
+    (device cos/sin vs glibc) and within the north-star tolerance (1e-4 m, 1e-5 rad) of its
+    PCL-faithful summation mode."""
+    src, tgt, nrm = synth.scan_pair(1_000_000, return_normals=True)
+    m = W.ICPMatcher(W.ICPMatcherParams(res=-1, estimator=W.EST_POINT_TO_PLANE))
+    m.setup(src, tgt)
+    m.setTargetNormals(nrm)
+    assert m.match() is True
+    nt = _host_threads()
+    ref = oracle.icp_align(src, tgt, estimator=oracle.EST_POINT_TO_PLANE, sum_mode=oracle.SUM_EXACT,
+                           target_normals=nrm, nn_threads=nt)
+    mse, ncorr, Ttr = m.trace()
+    assert ref.converged and m.iterations == ref.iterations
+    assert np.array_equal(ncorr, ref.n_corr)
+    assert np.array_equal(mse, ref.mse)
+    assert np.abs(Ttr - ref.T_trace).max() < 1e-7
+    assert np.abs(m.getResult() - ref.T.astype(np.float64)).max() < 1e-6
+    q, mm, d2 = m.correspondences()
+    assert np.array_equal(q, ref.corr_query)
+    assert np.array_equal(mm, ref.corr_match)
+    assert np.array_equal(d2, ref.corr_dist)
+    pcl = oracle.icp_align(src, tgt, estimator=oracle.EST_POINT_TO_PLANE, sum_mode=oracle.SUM_PCL,
+                           target_normals=nrm, nn_threads=nt)
+    assert m.iterations == pcl.iterations
+    assert np.abs(m.getResult()[:3, 3] - pcl.T[:3, 3]).max() < 1e-4
+    assert rot_angle(m.getResult()[:3, :3], pcl.T[:3, :3]) < 1e-5
+
+
+def test_icp_1m_svd_equals_oracle(W, oracle, synth):
+    """The reference's own estimator (SVD, icp.hpp:100) on the 1 M / 1 M pair: everything bit-exact
+    against the oracle's exact-sum mode, aligned cloud included."""
+    src, tgt = synth.scan_pair(1_000_000)
+    m = W.ICPMatcher(W.ICPMatcherParams(res=-1))
+    m.setup(src, tgt)
+    assert m.match() is True
+    nt = _host_threads()
+    ref = oracle.icp_align(src, tgt, sum_mode=oracle.SUM_EXACT, nn_threads=nt)
+    mse, ncorr, Ttr = m.trace()
+    assert m.iterations == ref.iterations
+    assert np.array_equal(ncorr, ref.n_corr) and np.array_equal(mse, ref.mse) and np.array_equal(Ttr, ref.T_trace)
+    assert np.array_equal(m.getResult().astype(np.float32), ref.T)
+    q, mm, d2 = m.correspondences()
+    assert np.array_equal(q, ref.corr_query) and np.array_equal(mm, ref.corr_match) and np.array_equal(d2, ref.corr_dist)
+    assert np.array_equal(m.aligned()[:, :3], ref.aligned[:, :3])
+    pcl = oracle.icp_align(src, tgt, sum_mode=oracle.SUM_PCL, nn_threads=nt)
+    assert np.abs(m.getResult()[:3, 3] - pcl.T[:3, 3]).max() < 1e-4
+    assert rot_angle(m.getResult()[:3, :3], pcl.T[:3, :3]) < 1e-5
+
+
+@pytest.mark.parametrize("scan_id", [0, 255])
+def test_batch_scan_200k_equals_oracle(W, oracle, synth, scan_id):
+    """BASELINE config 5: one 200 k-point scan-to-map alignment of the batch (first and last scan),
+    SVD estimator, bit-exact against the oracle."""
+    sources, target = synth.scan_batch(200_000, 0, ids=[scan_id])
+    src = sources[0]
+    m = W.ICPMatcher(W.ICPMatcherParams(res=-1))
+    m.setup(src, target)
+    ok = m.match()
+    ref = oracle.icp_align(src, target, sum_mode=oracle.SUM_EXACT, nn_threads=_host_threads())
+    assert ok == ref.converged and m.iterations == ref.iterations
+    mse, ncorr, Ttr = m.trace()
+    assert np.array_equal(ncorr, ref.n_corr) and np.array_equal(mse, ref.mse) and np.array_equal(Ttr, ref.T_trace)
+    assert np.array_equal(m.getResult().astype(np.float32), ref.T)
+    q, mm, d2 = m.correspondences()
+    assert np.array_equal(q, ref.corr_query) and np.array_equal(mm, ref.corr_match) and np.array_equal(d2, ref.corr_dist)
 
 
 def test_gicp_500k_recovers_rigid_copy(W, synth):

@@ -73,20 +73,44 @@ def test_ndt_reference_null_cases(W, oracle, testscan, res):
     assert rot_angle(m.getResult()[:3, :3], ref.T[:3, :3]) < 1e-5
 
 
-def test_ndt_first_steps_follow_oracle(W, oracle, testscan):
-    """smallDisplacement inputs (tests/ndt_tests.cpp:85-102, res = 0.3, 0.2 m): Newton on this score
-    is chaotic over 100 iterations (indefinite Hessians, no effective line search in PCL 1.8), so the
-    comparison is made where it is meaningful - after a few iterations."""
+def test_ndt_reference_small_displacement(W, oracle, testscan):
+    """smallDisplacement (tests/ndt_tests.cpp:85-102): res 0.3, target moved by 0.2 m in x, match()
+    true and ||result - perturb||_F < 0.12 - with the line search of PCL >= 1.9 (the default, see
+    wavecu.h); iteration count equal to the oracle's, transform within the north-star tolerance."""
+    T0 = np.eye(4)
+    T0[0, 3] = 0.2
+    tgt = pcl_transform(testscan, T0)
+    m = W.NDTMatcher(W.NDTMatcherParams(res=0.3))
+    m.setup(testscan, tgt)
+    assert m.match() is True
+    assert np.linalg.norm(m.getResult() - T0) < 0.12
+    ref = oracle.ndt_align(testscan, tgt, res=0.3)
+    assert ref.converged and m.iterations == ref.iterations
+    assert np.abs(m.getResult()[:3, 3] - ref.T[:3, 3]).max() < 1e-4
+    assert rot_angle(m.getResult()[:3, :3], ref.T[:3, :3]) < 1e-5
+
+
+def test_ndt_pcl18_first_steps_follow_oracle(W, oracle, testscan):
+    """The same inputs with PCL 1.8's skipped line search: a capped Newton iteration on indefinite
+    Hessians, chaotic over its 102 iterations, so the comparison is made where it is meaningful -
+    after a few steps."""
     T0 = np.eye(4)
     T0[0, 3] = 0.2
     tgt = pcl_transform(testscan, T0)
     for iters in (1, 2, 3):
-        m = W.NDTMatcher(W.NDTMatcherParams(res=0.3, max_iter=iters - 2))  # stops after `iters` Newton steps
+        m = W.NDTMatcher(W.NDTMatcherParams(res=0.3, max_iter=iters - 2, line_search=W.NDT_LS_PCL18))
         m.setup(testscan, tgt)
         m.match()
-        ref = oracle.ndt_align(testscan, tgt, res=0.3, max_iter=iters - 2)
+        ref = oracle.ndt_align(testscan, tgt, res=0.3, max_iter=iters - 2, line_search=oracle.NDT_LS_PCL18)
         assert m.iterations == ref.iterations == iters
         assert np.abs(m.getResult() - ref.T).max() < 1e-5
+
+
+def test_ndt_stats_counts_cells(W, oracle, testscan):
+    m = W.NDTMatcher(W.NDTMatcherParams(res=0.5))
+    m.setup(testscan, testscan.copy())
+    voxel = m.grid()[0]
+    assert m.stats()["n_cells"] == len(voxel) == len(oracle.ndt_grid(testscan, 0.5)[0])
 
 
 def test_ndt_degenerate_inputs(W, testscan):

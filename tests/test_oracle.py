@@ -172,3 +172,19 @@ def test_information_matrix_properties(oracle, testscan):
     a, _ = oracle.estimate_lum_old(r.last.aligned, r.ds_tgt, 3.0, oracle.SUM_EXACT, k_quad, nn_threads=4)
     b, _ = oracle.estimate_lum_old(r.last.aligned, r.ds_tgt, 3.0, oracle.SUM_PCL, k_quad, nn_threads=4)
     assert np.allclose(a, b, rtol=1e-4)
+
+
+def test_fix128_small_negative_sums_convert_exactly(oracle):
+    """The 128-bit totals are converted sign-magnitude: a small negative total keeps its low bits
+    (two's-complement halves would round 2^64 - |v| to 53 bits first and return 0 for -5 units)."""
+    assert oracle.fix128_sum([-5.0], 0) == -5.0
+    assert oracle.fix128_sum([3.0, -8.0], 0) == -5.0
+    assert oracle.fix128_sum([-5.0 * 2.0 ** -47], 47) == -5.0 * 2.0 ** -47
+    big = 2.0 ** 40
+    assert oracle.fix128_sum([big, -big, -1.25], 20) == -1.25
+    rng = np.random.default_rng(5)
+    t = rng.normal(0, 50.0, 100_000)
+    k = 30
+    exact = sum(int(np.rint(np.ldexp(v, k))) for v in t)      # Python integers: exact
+    assert oracle.fix128_sum(t, k) == float(exact) / 2.0 ** k
+    assert oracle.fix128_sum(-np.abs(t), k) == -oracle.fix128_sum(np.abs(t), k)

@@ -63,11 +63,36 @@ def test_ndt_derivatives_match_finite_differences(oracle, testscan):
         assert np.abs((gp - gm) / 2e-5 - H1[:, i]).max() < 0.02 * np.abs(H1[:, :3]).max()
 
 
-def test_ndt_reference_null_case(oracle, testscan):
-    """nullDisplacement (tests/ndt_tests.cpp:64-82): identical clouds, res 0.1 -> ||T - I||_F < 0.12.
-    With t_eps = 1e-8 PCL never meets its step criterion here and stops on the iteration cap."""
-    r = oracle.ndt_align(testscan, testscan.copy(), res=0.1)
+def test_ndt_reference_null_cases(oracle, testscan):
+    """fullResNullMatch (res 0.05 from tests/config/ndt.yaml) and nullDisplacement (res 0.1),
+    tests/ndt_tests.cpp:45-82: identical clouds -> ||T - I||_F < 0.12.  With PCL >= 1.9's line
+    search the step criterion (t_eps = 1e-8) is met after a few iterations; with PCL 1.8's skipped
+    search the Newton step never gets that short and the match stops on the iteration cap."""
+    for res, iters in ((0.05, 3), (0.1, 4)):
+        r = oracle.ndt_align(testscan, testscan.copy(), res=res)
+        assert r.converged and r.iterations == iters
+        assert np.linalg.norm(r.T - np.eye(4)) < 1e-3
+    r = oracle.ndt_align(testscan, testscan.copy(), res=0.1, line_search=oracle.NDT_LS_PCL18)
     assert r.converged and r.iterations == 102
-    assert np.linalg.norm(r.T - np.eye(4)) < 0.12
     assert np.linalg.norm(r.T - np.eye(4)) < 1e-3
     assert not oracle.ndt_align(np.zeros((0, 3), np.float32), testscan, res=1.0).converged
+
+
+def test_ndt_reference_small_displacement(oracle, testscan):
+    """smallDisplacement (tests/ndt_tests.cpp:85-102): target = scan moved by 0.2 m in x, res 0.3,
+    match() true and ||T - T_true||_F < 0.12.  This case decides which PCL release the restatement
+    must follow: with computeStepLengthMT as PCL >= 1.9 has it (the More-Thuente search runs) the
+    match converges in 13 iterations, 6e-5 from the truth; with PCL 1.8's `interval_converged =
+    (step_max - step_min) > 0` the search is skipped, the capped Newton steps on this score's
+    indefinite Hessians wander, and the match ends on the iteration cap metres away - it would fail
+    the reference's own assertion."""
+    T0 = np.eye(4)
+    T0[0, 3] = 0.2
+    tgt = pcl_transform(testscan, T0)
+    r = oracle.ndt_align(testscan, tgt, res=0.3)
+    assert r.converged and r.iterations == 13
+    assert np.linalg.norm(r.T - T0) < 0.12          # the reference's bound
+    assert np.linalg.norm(r.T - T0) < 1e-3
+    old = oracle.ndt_align(testscan, tgt, res=0.3, line_search=oracle.NDT_LS_PCL18)
+    assert old.converged and old.iterations == 102
+    assert np.linalg.norm(old.T - T0) > 0.12
