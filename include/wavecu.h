@@ -106,6 +106,14 @@ int wavecu_icp_set_source_device(wavecu_icp *h, const void *d_xyzw, size_t n);
 int wavecu_icp_set_target_device(wavecu_icp *h, const void *d_xyzw, size_t n);
 int wavecu_icp_set_target_normals_device(wavecu_icp *h, const void *d_nxyzw, size_t n);
 
+/* Which kernel runs the per-iteration exact 1-NN search (results are identical bit for bit):
+ * WAVECU_SEARCH_TREE - one query per lane walking the LBVH (default); WAVECU_SEARCH_TILED - a CTA per
+ * tile of Morton-consecutive queries, target runs staged into shared memory with cp.async.bulk, the
+ * tree walk only for the queries the tile cannot certify (csrc/tile_nn.cuh).  The environment variable
+ * WAVECU_NN=tile|walk sets the default of new handles. */
+enum { WAVECU_SEARCH_TREE = 0, WAVECU_SEARCH_TILED = 1 };
+int wavecu_icp_set_search(wavecu_icp *h, int mode);
+
 /* One pcl align(): (re)builds the target search structure if the target changed, iterates on
  * the device, returns final_transformation_ (fp32 values widened to double, row major). */
 int wavecu_icp_align(wavecu_icp *h, double T_out[16], int *converged, int *iterations, int *state);
@@ -134,6 +142,7 @@ typedef struct {
     long long iterate_launches;
     long long kernel_launches; /* every kernel this library launched in the call */
     long long pairs;        /* sum over iterations of source points queried */
+    long long fallback_queries; /* of which the tiled kernel could not certify and finished with the tree walk */
 } wavecu_stats;
 int wavecu_icp_set_profiling(wavecu_icp *h, int enabled);
 int wavecu_icp_stats(wavecu_icp *h, wavecu_stats *out);

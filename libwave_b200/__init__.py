@@ -6,5 +6,5 @@ scan generator used by the tests and the bench.  Nothing here imports ``oracle/`
 """
 from .matching import (EST_POINT_TO_PLANE, EST_SVD, INFO_CENSI, INFO_LUM, INFO_LUMOLD, GICPMatcher,  # noqa: F401
                        GICPMatcherParams, ICPMatcher,
-                       ICPMatcherParams, Matcher, NDTMatcher, NDTMatcherParams, NDT_LS_MORE_THUENTE, NDT_LS_PCL18,
+                       ICPMatcherParams, Matcher, NDTMatcher, NDTMatcherParams, NDT_LS_MORE_THUENTE, NDT_LS_PCL18, SEARCH_TILED, SEARCH_TREE,
                        NearestNeighbour, voxel_grid)

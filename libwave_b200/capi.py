@@ -41,7 +41,7 @@ class GicpParamsC(C.Structure):
 class StatsC(C.Structure):
     _fields_ = [("build_ms", C.c_double), ("iterate_ms", C.c_double), ("solve_ms", C.c_double),
                 ("total_ms", C.c_double), ("iterate_launches", C.c_longlong), ("kernel_launches", C.c_longlong),
-                ("pairs", C.c_longlong)]
+                ("pairs", C.c_longlong), ("fallback_queries", C.c_longlong)]
 
 
 _fp, _ip, _dp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -73,6 +73,7 @@ SIGNATURES = {
     "wavecu_nn_set_target": (C.c_int, [_vp, _fp, _sz]),
     "wavecu_nn_search": (C.c_int, [_vp, _fp, _sz, C.c_double, _ip, _fp]),
     "wavecu_nn_search_device": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, C.c_int, _fp]),
+    "wavecu_icp_set_search": (C.c_int, [_vp, C.c_int]),
     "wavecu_ndt_default_params": (None, [C.POINTER(NdtParamsC)]),
     "wavecu_ndt_create": (C.c_int, [C.POINTER(NdtParamsC), C.c_int, _vp, C.POINTER(_vp)]),
     "wavecu_ndt_destroy": (C.c_int, [_vp]),

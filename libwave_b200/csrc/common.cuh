@@ -52,6 +52,7 @@ struct IcpState {
     int state;
     int n_corr;
     int pad;
+    long long fb_total;   // queries the tiled correspondence kernel handed to the LBVH walk, summed over the iterations
 };
 
 struct TraceRow {

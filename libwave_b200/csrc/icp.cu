@@ -7,12 +7,14 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../include/wavecu.h"
 #include "icp_kernels.cuh"
 #include "index.cuh"
 #include "info_kernels.cuh"
+#include "tile_nn.cuh"
 #include "voxel.cuh"
 
 namespace wavecu {
@@ -25,6 +27,7 @@ struct SetupArgs {
     IcpState *st;
     Acc128 *acc;
     double max_corr;
+    int *fb_count;
 };
 
 __device__ double bbox_max_abs(const unsigned *bb) {
@@ -45,6 +48,7 @@ __global__ void setup_kernel(SetupArgs a) {
         a.acc[i].hi = 0;
     }
     if (t != 0) return;
+    if (a.fb_count) *a.fb_count = 0;
     MatchConsts &mc = *a.mc;
     for (int d = 0; d < 3; ++d) {
         mc.src_lo[d] = ordered_to_float(a.src_bbox[d]);
@@ -81,6 +85,7 @@ __global__ void setup_kernel(SetupArgs a) {
     st.converged = 0;
     st.state = WAVECU_CONV_NOT_CONVERGED;
     st.n_corr = 0;
+    st.fb_total = 0;
 }
 
 __global__ void fill_int_kernel(int *p, int v, size_t n) {
@@ -152,6 +157,9 @@ struct IcpHandle {
     Acc128 *d_acc = nullptr;
     TraceRow *d_trace = nullptr;
     int trace_cap = 0;
+    // tiled correspondence kernel (tile_nn.cuh): queries it hands to the LBVH walk
+    bool use_tile = false;
+    int *d_fb_count = nullptr, *d_fb_list = nullptr;
 
     // pinned host mirrors
     int *h_progress = nullptr;  // mapped: (launch number << 1) | done, written by the solve kernel
@@ -228,6 +236,12 @@ int IcpHandle::init() {
     WCU_CHECK(cudaEventCreateWithFlags(&ev_src_sorted, getenv("WAVECU_TIMELINE") ? cudaEventDefault
                                                                                   : cudaEventDisableTiming));
     WCU_CHECK(cudaEventCreate(&ev_first));
+    if (const char *e = getenv("WAVECU_NN")) use_tile = std::string(e) == "tile";   // default of wavecu_icp_set_search
+    tgt.want_boxes = use_tile;
+    WCU_CHECK(cudaFuncSetAttribute(correspond_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) sizeof(TileSmem)));
+    WCU_CHECK(cudaMalloc((void **) &d_fb_count, sizeof(int)));
+    WCU_CHECK(cudaMemset(d_fb_count, 0, sizeof(int)));
     src.device = tgt.cloud.device = device;
     src.stream = aux;
     tgt.cloud.stream = stream;
@@ -348,9 +362,9 @@ int IcpHandle::set_target_normals(const float *nxyzw, size_t n, bool from_device
 int IcpHandle::ensure_iter_buffers(size_t n_src_pad, int max_iter) {
     if (n_src_pad > iter_cap) {
         for (void *p : {(void *) d_nn_pos, (void *) d_nn_idx, (void *) d_nn_d2, (void *) d_out_idx, (void *) d_out_d2,
-                        (void *) d_aligned})
+                        (void *) d_aligned, (void *) d_fb_list})
             if (p) WCU_CHECK(cudaFree(p));
-        d_nn_pos = d_nn_idx = d_out_idx = nullptr;
+        d_nn_pos = d_nn_idx = d_out_idx = d_fb_list = nullptr;
         d_nn_d2 = d_out_d2 = nullptr;
         d_aligned = nullptr;
         iter_cap = 0;
@@ -361,6 +375,7 @@ int IcpHandle::ensure_iter_buffers(size_t n_src_pad, int max_iter) {
         WCU_CHECK(cudaMalloc((void **) &d_out_idx, a * sizeof(int)));
         WCU_CHECK(cudaMalloc((void **) &d_out_d2, a * sizeof(float)));
         WCU_CHECK(cudaMalloc((void **) &d_aligned, a * sizeof(float4)));
+        WCU_CHECK(cudaMalloc((void **) &d_fb_list, a * sizeof(int)));
         iter_cap = a;
     }
     if (max_iter > trace_cap) {
@@ -440,7 +455,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         fill_int_kernel<<<(unsigned) ((n_src + 255) / 256), 256, 0, stream>>>(d_nn_pos, -1, n_src);
         ++extra_launches;
     }
-    SetupArgs sa{src.d_bbox, tgt.cloud.d_bbox, d_mc, d_st, d_acc, prm.max_corr};
+    SetupArgs sa{src.d_bbox, tgt.cloud.d_bbox, d_mc, d_st, d_acc, prm.max_corr, d_fb_count};
     setup_kernel<<<1, 256, 0, stream>>>(sa);
     ++extra_launches;
     WCU_CHECK(cudaGetLastError());
@@ -462,8 +477,12 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     int *d_progress = nullptr;
     WCU_CHECK(cudaHostGetDevicePointer((void **) &d_progress, h_progress, 0));
     *(volatile int *) h_progress = 0;
-    SolveArgs so{d_st, d_mc, d_acc, d_trace, max_iter, prm.t_eps, prm.fit_eps, d_progress, 0};
+    SolveArgs so{d_st, d_mc, d_acc, d_trace, max_iter, prm.t_eps, prm.fit_eps, d_progress, 0, d_fb_count};
     const unsigned grid_nn = (unsigned) std::max<size_t>(1, (n_src + kIterThreads - 1) / kIterThreads);
+    const bool tiled = use_tile && tgt.want_boxes;
+    const unsigned grid_tile = (unsigned) std::max<size_t>(1, (n_src + kTileQ - 1) / kTileQ);
+    const unsigned grid_fb = std::min<unsigned>(grid_nn, 148u * 8u);
+    const TileFallback fb{d_fb_count, d_fb_list};
     const unsigned grid_red = (unsigned) std::max<size_t>(1, (n_src + kReduceThreads - 1) / kReduceThreads);
     std::vector<cudaEvent_t> it_ev;
     int launched = 0;
@@ -473,7 +492,12 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             it_ev.push_back(next_event());
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
         }
-        correspond_kernel<<<grid_nn, kIterThreads, 0, stream>>>(ia);
+        if (tiled) {
+            correspond_tile_kernel<<<grid_tile, kTileQ, sizeof(TileSmem), stream>>>(ia, tgt.boxes, fb);
+            tile_fallback_kernel<<<grid_fb, kIterThreads, 0, stream>>>(ia, fb);
+        } else {
+            correspond_kernel<<<grid_nn, kIterThreads, 0, stream>>>(ia);
+        }
         if (profiling) {
             it_ev.push_back(next_event());
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
@@ -541,8 +565,9 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     result_n_src = n_src;
 
     stats.iterate_launches = last.iter;
-    stats.kernel_launches = (src.launches + tgt.cloud.launches - launches0) + extra_launches + 3LL * launched;
+    stats.kernel_launches = (src.launches + tgt.cloud.launches - launches0) + extra_launches + (tiled ? 4LL : 3LL) * launched;
     stats.pairs = (long long) last.iter * (long long) n_src;
+    stats.fallback_queries = last.fb_total;
     if (profiling) {
         float ms = 0;
         // the build may have been queued by set_source / set_target already: count from the first of them
@@ -1045,7 +1070,8 @@ void IcpHandle::release() {
     src.release();
     tgt.release();
     for (void *p : {(void *) d_nn_pos, (void *) d_nn_idx, (void *) d_nn_d2, (void *) d_out_idx, (void *) d_out_d2,
-                    (void *) d_aligned, (void *) d_mc, (void *) d_st, (void *) d_acc, (void *) d_trace})
+                    (void *) d_aligned, (void *) d_mc, (void *) d_st, (void *) d_acc, (void *) d_trace,
+                    (void *) d_fb_count, (void *) d_fb_list})
         if (p) cudaFree(p);
     vox.release();
     for (void *p : {(void *) d_orig_src, (void *) d_orig_tgt, (void *) d_pos2})
@@ -1224,6 +1250,17 @@ int wavecu_icp_trace(wavecu_icp *w, double *mse, int *n_corr, float *T_inc, int 
 int wavecu_icp_info(wavecu_icp *w, int method, double info_out[36]) {
     if (!w || !info_out) return WAVECU_ERR_ARG;
     return w->h.info(method, info_out);
+}
+
+int wavecu_icp_set_search(wavecu_icp *w, int mode) {
+    if (!w || (mode != WAVECU_SEARCH_TREE && mode != WAVECU_SEARCH_TILED)) return WAVECU_ERR_ARG;
+    const bool tile = mode == WAVECU_SEARCH_TILED;
+    if (tile != w->h.use_tile) {
+        w->h.use_tile = tile;
+        w->h.tgt.want_boxes = tile;
+        if (tile) w->h.tgt.dirty = true;   // the box pyramid is built with the tree
+    }
+    return WAVECU_OK;
 }
 
 int wavecu_icp_set_profiling(wavecu_icp *w, int enabled) {

@@ -229,6 +229,7 @@ struct SolveArgs {
     // putting a copy or an event between the kernels
     volatile int *progress;
     int launch;
+    int *fb_count;   // fallback list length of the tiled correspondence kernel: cleared for the next iteration
 };
 
 // (a posted store: nothing waits for it - it is visible to the host at the latest when the kernel ends)
@@ -376,6 +377,10 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
     __syncthreads();
     if (threadIdx.x != 0) return;
     IcpState &st = *a.st;
+    if (a.fb_count) {
+        st.fb_total += *a.fb_count;
+        *a.fb_count = 0;
+    }
     const MatchConsts &mc = *a.mc;
     auto val = [&](int i, int /*k*/) { return s_val[i]; };
     const long long n = (long long) s_lo[NV];

@@ -260,6 +260,52 @@ __global__ void __launch_bounds__(128) normals_kernel(NnIndex ix, int n, int k, 
     nrm[s] = make_float4((float) nx, (float) ny, (float) nz, 0.f);
 }
 
+// Box pyramid, levels 0 and 1: one thread per run of 8 sorted points (its 128 B are contiguous), then
+// the 8 threads of a 64-point run combine their boxes with shuffles.  n_pad is a multiple of 64.
+__global__ void __launch_bounds__(kBuildThreads) boxes_low_kernel(const float4 *__restrict__ pts, int n_runs8,
+                                                                  float4 *lv0, float4 *lv1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // n_runs8 is a multiple of 8: whole groups of 8 lanes exit together
+    if (i >= n_runs8) return;
+    float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 p = pts[(size_t) i * 8 + k];
+        lox = fminf(lox, p.x); loy = fminf(loy, p.y); loz = fminf(loz, p.z);
+        hix = fmaxf(hix, p.x); hiy = fmaxf(hiy, p.y); hiz = fmaxf(hiz, p.z);
+    }
+    lv0[2 * (size_t) i] = make_float4(lox, loy, loz, 0.f);
+    lv0[2 * (size_t) i + 1] = make_float4(hix, hiy, hiz, 0.f);
+    const unsigned group = 0xffu << ((threadIdx.x & 31) & ~7);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        lox = fminf(lox, __shfl_xor_sync(group, lox, o)); loy = fminf(loy, __shfl_xor_sync(group, loy, o));
+        loz = fminf(loz, __shfl_xor_sync(group, loz, o)); hix = fmaxf(hix, __shfl_xor_sync(group, hix, o));
+        hiy = fmaxf(hiy, __shfl_xor_sync(group, hiy, o)); hiz = fmaxf(hiz, __shfl_xor_sync(group, hiz, o));
+    }
+    if ((i & 7) == 0) {
+        lv1[2 * (size_t) (i >> 3)] = make_float4(lox, loy, loz, 0.f);
+        lv1[2 * (size_t) (i >> 3) + 1] = make_float4(hix, hiy, hiz, 0.f);
+    }
+}
+
+// Levels >= 2, one level per launch (they shrink by 8 each: a handful of short launches inside the
+// build graph); a missing child (the last box of a level) is skipped.
+__global__ void __launch_bounds__(kBuildThreads) boxes_up_kernel(const float4 *__restrict__ child, int n_child,
+                                                                 float4 *parent, int n_parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_parent) return;
+    float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
+    for (int k = 0; k < 8; ++k) {
+        const int c = i * 8 + k;
+        if (c >= n_child) break;
+        const float4 lo = child[2 * (size_t) c], hi = child[2 * (size_t) c + 1];
+        lox = fminf(lox, lo.x); loy = fminf(loy, lo.y); loz = fminf(loz, lo.z);
+        hix = fmaxf(hix, hi.x); hiy = fmaxf(hiy, hi.y); hiz = fmaxf(hiz, hi.z);
+    }
+    parent[2 * (size_t) i] = make_float4(lox, loy, loz, 0.f);
+    parent[2 * (size_t) i + 1] = make_float4(hix, hiy, hiz, 0.f);
+}
+
 template <class T>
 int grow(T *&ptr, size_t &cap, size_t want) {
     if (want <= cap) return WAVECU_OK;
@@ -559,9 +605,41 @@ int TargetIndex::build() {
     }
     if (!d_root) WCU_CHECK(cudaMalloc((void **) &d_root, sizeof(TreeRoot)));
     if (kCellBits > 0 && !d_cells) WCU_CHECK(cudaMalloc((void **) &d_cells, kCellCount * sizeof(CellEntry)));
-    int rc = cloud.pre_sort(std::max<size_t>(n, 1));
+    int rc = cloud.pre_sort(std::max<size_t>(sorted_pad(), 1));
     if (rc) return rc;
-    const unsigned long long key[8] = {(unsigned long long) n, (unsigned long long) (uintptr_t) cloud.d_raw,
+    if (want_boxes) {
+        // level sizes: 8-point runs, then /8 per level until at most kBoxTop boxes (at least two levels)
+        size_t total = 0;
+        int cnt[kBoxLevelsMax], nl = 0;
+        size_t c = sorted_pad() / 8;
+        for (;;) {
+            cnt[nl++] = (int) c;
+            total += 2 * c;
+            if ((nl >= 2 && c <= (size_t) kBoxTop) || nl == kBoxLevelsMax) break;
+            c = (c + 7) / 8;
+        }
+        if (cnt[nl - 1] > kBoxTop) {
+            set_last_error("target cloud too large for the box pyramid");
+            return WAVECU_ERR_ARG;
+        }
+        if (total > boxes_cap) {
+            if (d_boxes) WCU_CHECK(cudaFree(d_boxes));
+            d_boxes = nullptr;
+            boxes_cap = 0;
+            const size_t a = total + total / 8 + 64;
+            WCU_CHECK(cudaMalloc((void **) &d_boxes, a * sizeof(float4)));
+            boxes_cap = a;
+        }
+        size_t off = 0;
+        for (int k = 0; k < kBoxLevelsMax; ++k) {
+            boxes.lv[k] = k < nl ? d_boxes + off : nullptr;
+            boxes.cnt[k] = k < nl ? cnt[k] : 0;
+            if (k < nl) off += 2 * (size_t) cnt[k];
+        }
+        boxes.n_levels = nl;
+    }
+    const unsigned long long key[8] = {(unsigned long long) n + ((unsigned long long) want_boxes << 62),
+                                       (unsigned long long) (uintptr_t) cloud.d_raw ^ ((unsigned long long) (uintptr_t) d_boxes << 1),
                                        (unsigned long long) (uintptr_t) cloud.d_sorted,
                                        (unsigned long long) (uintptr_t) cloud.d_keys,
                                        (unsigned long long) (uintptr_t) d_nodes, (unsigned long long) (uintptr_t) d_other,
@@ -579,8 +657,20 @@ int TargetIndex::build() {
 // Morton sort + one-launch radix-tree construction, as one capturable launch sequence
 int TargetIndex::enqueue_build() {
     const size_t n = cloud.n;
-    int rc = cloud.enqueue_sort(std::max<size_t>(n, 1), nullptr, nullptr);
+    int rc = cloud.enqueue_sort(std::max<size_t>(sorted_pad(), 1), nullptr, nullptr);
     if (rc) return rc;
+    if (want_boxes && n) {
+        const int runs8 = boxes.cnt[0];
+        boxes_low_kernel<<<(unsigned) ((runs8 + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, cloud.stream>>>(
+            cloud.d_sorted, runs8, const_cast<float4 *>(boxes.lv[0]), const_cast<float4 *>(boxes.lv[1]));
+        ++cloud.launches;
+        for (int k = 2; k < boxes.n_levels; ++k) {
+            boxes_up_kernel<<<(unsigned) ((boxes.cnt[k] + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0,
+                              cloud.stream>>>(boxes.lv[k - 1], boxes.cnt[k - 1], const_cast<float4 *>(boxes.lv[k]),
+                                              boxes.cnt[k]);
+            ++cloud.launches;
+        }
+    }
     if (n) WCU_CHECK(cudaMemsetAsync(d_other, 0xff, n * sizeof(int), cloud.stream));
     CellEntry *cells = (kCellBits > 0 && cloud.key_bits >= kCellBits) ? d_cells : nullptr;
     if (cells) WCU_CHECK(cudaMemsetAsync(cells, 0x80, kCellCount * sizeof(CellEntry), cloud.stream));  // kCellEmpty
@@ -615,9 +705,11 @@ void TargetIndex::release() {
     build_graph.release();
     cloud.release();
     for (void *p : {(void *) d_nodes, (void *) d_other, (void *) d_root, (void *) d_nrm_raw, (void *) d_nrm_sorted,
-                    (void *) d_cells})
+                    (void *) d_cells, (void *) d_boxes})
         if (p) cudaFree(p);
     d_cells = nullptr;
+    d_boxes = nullptr;
+    boxes_cap = 0;
     if (ev_nrm_up) cudaEventDestroy(ev_nrm_up);
     ev_nrm_up = nullptr;
     nrm_up_pending = nrm_dirty = false;

@@ -219,6 +219,10 @@ class ICPMatcher(Matcher):
     def set_profiling(self, on: bool):
         capi.check(self._L.wavecu_icp_set_profiling(self._h, int(on)))
 
+    def set_search(self, mode: int):
+        """SEARCH_TREE (LBVH walk, default) or SEARCH_TILED (shared-memory tiles, csrc/tile_nn.cuh)."""
+        capi.check(self._L.wavecu_icp_set_search(self._h, int(mode)))
+
     def stats(self) -> dict:
         s = capi.StatsC()
         capi.check(self._L.wavecu_icp_stats(self._h, C.byref(s)))
@@ -316,6 +320,7 @@ class NDTMatcherParams:
 
 
 NDT_LS_PCL18, NDT_LS_MORE_THUENTE = 0, 1
+SEARCH_TREE, SEARCH_TILED = 0, 1
 
 
 class NDTMatcher(Matcher):
