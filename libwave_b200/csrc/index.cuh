@@ -110,12 +110,31 @@ struct TreeRoot {
     float4 lo, hi;   // box of all finite points; lo.w = link (int bits), hi.w = count (int bits)
 };
 
+// Box pyramid over the Morton-sorted target for the tiled correspondence kernel (tile_nn.cuh): level 0
+// holds the bounding box of every run of 8 consecutive sorted points, level k the box of 8 level k-1
+// boxes (level 1 = 64 points: the unit that is staged into shared memory).  Box i of level k is the pair
+// (lv[k][2 i], lv[k][2 i + 1]) = (lo, hi), xyz used.  Runs are contiguous in the sorted array, so a
+// level-1 box names one 1 KB slice of points and one 256 B slice of level-0 boxes - bulk-copy units.
+// Pads (+inf points behind the last finite one) give +inf box corners, which no query reaches.
+constexpr int kBoxLevelsMax = 10;
+constexpr int kBoxTop = 128;      // the top level has at most this many boxes
+struct BoxLevels {
+    const float4 *lv[kBoxLevelsMax];
+    int cnt[kBoxLevelsMax];
+    int n_levels;                 // >= 2
+};
+
 struct TargetIndex {
     MortonCloud cloud;
     TNode *d_nodes = nullptr;    // n-1 records, indexed by split position
     int *d_other = nullptr;      // n-1 rendezvous slots of the bottom-up build
     TreeRoot *d_root = nullptr;
     CellEntry *d_cells = nullptr;   // kCellCount entries, rebuilt with the tree
+    bool want_boxes = false;        // also build the box pyramid (ICP: the tiled correspondence kernel)
+    float4 *d_boxes = nullptr;      // all levels, level 0 first
+    size_t boxes_cap = 0;           // in float4
+    BoxLevels boxes{};              // device pointers into d_boxes; valid when want_boxes and !dirty
+    size_t sorted_pad() const { return want_boxes ? ((cloud.n + 63) / 64) * 64 : cloud.n; }
     float4 *d_nrm_raw = nullptr, *d_nrm_sorted = nullptr;  // optional normals
     size_t nrm_n = 0;
     size_t node_cap = 0, nrm_cap = 0, nrm_sorted_cap = 0;
