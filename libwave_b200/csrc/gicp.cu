@@ -33,6 +33,8 @@ namespace {
 
 struct GicpPose {
     float T[16];
+    double scale;   // 2^k of the fixed-point cost sums
+    int k;
 };
 
 constexpr int kGicpThreads = 128;
@@ -150,15 +152,26 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *_
                                                                  const float4 *__restrict__ tgt_sorted,
                                                                  const int *__restrict__ pos,
                                                                  const double *__restrict__ mahal, GicpPose pose,
-                                                                 double *partial, unsigned *ticket,
+                                                                 long long *partial, unsigned *ticket,
                                                                  volatile double *host_sums, volatile int *host_seq,
                                                                  int seq) {
     __shared__ float T[12];
     if (threadIdx.x < 12) T[threadIdx.x] = pose.T[threadIdx.x];
     __syncthreads();
-    double acc[kCostVals];
+    // Exact sums (same spec as the oracle's fdf and as the ICP estimator): every term is
+    // rounded once to a multiple of 2^-k, clamped to +-2^52 units, and added as an integer - per thread
+    // (<= 16 terms: the grid grows with the cloud), per warp, per block in 64 bits, over the blocks in
+    // 128 bits.  Integer addition is associative, so the result is independent of the Morton order and
+    // of which block finishes last, and equal to the oracle's bit for bit.
+    long long acc[kCostVals];
 #pragma unroll
-    for (int i = 0; i < kCostVals; ++i) acc[i] = 0.0;
+    for (int i = 0; i < kCostVals; ++i) acc[i] = 0;
+    const double scale = pose.scale;
+    auto fix = [&](double v) -> long long {
+        v = v * scale;
+        v = fmin(fmax(v, -4503599627370496.0), 4503599627370496.0);
+        return __double2ll_rn(v);
+    };
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_src; s += gridDim.x * blockDim.x) {
         const int j = pos[s];
         if (j < 0) continue;
@@ -169,33 +182,32 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *_
         const double *M = mahal + 9 * (size_t) s;
         const double t0 = (M[0] * r0 + M[1] * r1) + M[2] * r2, t1 = (M[3] * r0 + M[4] * r1) + M[5] * r2,
                      t2 = (M[6] * r0 + M[7] * r1) + M[8] * r2;
-        acc[0] += (r0 * t0 + r1 * t1) + r2 * t2;
-        acc[1] += t0;
-        acc[2] += t1;
-        acc[3] += t2;
+        acc[0] += fix((r0 * t0 + r1 * t1) + r2 * t2);
+        acc[1] += fix(t0);
+        acc[2] += fix(t1);
+        acc[3] += fix(t2);
         const double b0 = p.x, b1 = p.y, b2 = p.z;  // base_transformation_ (identity) * p_src
-        acc[4] += b0 * t0; acc[5] += b0 * t1; acc[6] += b0 * t2;
-        acc[7] += b1 * t0; acc[8] += b1 * t1; acc[9] += b1 * t2;
-        acc[10] += b2 * t0; acc[11] += b2 * t1; acc[12] += b2 * t2;
-        acc[13] += 1.0;
+        acc[4] += fix(b0 * t0); acc[5] += fix(b0 * t1); acc[6] += fix(b0 * t2);
+        acc[7] += fix(b1 * t0); acc[8] += fix(b1 * t1); acc[9] += fix(b1 * t2);
+        acc[10] += fix(b2 * t0); acc[11] += fix(b2 * t1); acc[12] += fix(b2 * t2);
+        acc[13] += 1;
     }
-    __shared__ double s_red[kGicpThreads / 32][kCostVals];
+    __shared__ long long s_red[kGicpThreads / 32][kCostVals];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < kCostVals; ++i) {
-        double v = acc[i];
+        long long v = acc[i];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) s_red[warp][i] = v;
     }
     __syncthreads();
     if (threadIdx.x < kCostVals) {
-        double v = 0;
+        long long v = 0;
         for (int w = 0; w < kGicpThreads / 32; ++w) v += s_red[w][threadIdx.x];
         partial[(size_t) blockIdx.x * kCostVals + threadIdx.x] = v;
     }
-    // The last block to arrive adds the block rows in block order (the result does not depend on
-    // which block that is) and hands the 14 sums to the host through mapped memory: one launch and
-    // no copy per BFGS evaluation, of which a match makes several hundred.
+    // The last block to arrive adds the block rows and hands the 14 sums to the host through mapped
+    // memory: one launch and no copy per BFGS evaluation, of which a match makes several hundred.
     __shared__ bool s_last;
     __threadfence();
     __syncthreads();
@@ -203,9 +215,10 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *_
     __syncthreads();
     if (!s_last) return;
     if (threadIdx.x < kCostVals) {
-        double v = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partial + (size_t) b * kCostVals + threadIdx.x);
-        host_sums[threadIdx.x] = v;
+        __int128 v = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += (__int128) __ldcg(partial + (size_t) b * kCostVals + threadIdx.x);
+        host_sums[threadIdx.x] = threadIdx.x == 13 ? (double) (long long) v
+                                                   : acc_to_double((unsigned long long) v, (long long) (v >> 64), pose.k);
     }
     __threadfence_system();
     __syncthreads();
@@ -305,7 +318,10 @@ struct GicpHandle {
     size_t src_cap = 0, tgt_cap = 0;
     bool cov_src_ok = false, cov_tgt_ok = false;
     GicpIterConsts *d_consts = nullptr;
-    double *d_partial = nullptr, *h_sums = nullptr;  // h_sums: mapped host memory
+    long long *d_partial = nullptr;   // per-block fixed-point partial sums of the cost kernel
+    size_t partial_blocks = 0;
+    double *h_sums = nullptr;         // mapped host memory
+    int sum_k = 28;                   // fixed-point exponent of the cost sums of the current match
     unsigned *d_ticket = nullptr;
     int *h_seq = nullptr;   // mapped: number of the last evaluation whose sums are in h_sums
     int cost_seq = 0;
@@ -325,7 +341,6 @@ struct GicpHandle {
         src.cloud.device = tgt.cloud.device = vox.device = device;
         src.cloud.stream = tgt.cloud.stream = vox.stream = stream;
         WCU_CHECK(cudaMalloc((void **) &d_consts, sizeof(GicpIterConsts)));
-        WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(double) * kCostVals * (size_t) n_blocks));
         WCU_CHECK(cudaHostAlloc((void **) &h_sums, sizeof(double) * kCostVals, cudaHostAllocMapped));
         WCU_CHECK(cudaHostAlloc((void **) &h_seq, sizeof(int), cudaHostAllocMapped));
         *h_seq = 0;
@@ -422,6 +437,8 @@ struct GicpHandle {
         apply_state(T, x);
         GicpPose pose;
         std::memcpy(pose.T, T, sizeof T);
+        pose.k = sum_k;
+        pose.scale = std::ldexp(1.0, sum_k);
         ++evaluations;
         const int seq = ++cost_seq;
         gicp_cost_kernel<<<n_blocks, kGicpThreads, 0, stream>>>(src.cloud.d_sorted, (int) src.cloud.n, tgt.cloud.d_sorted,
@@ -747,6 +764,30 @@ int GicpHandle::match(double *T_out, int *converged_out, int *iterations_out) {
     if (n_src && n_tgt) {
         int rc = prepare();
         if (rc) return rc;
+        // cost-kernel grid: at most 16 pairs per thread (64-bit partial sums), at least four blocks per SM
+        n_blocks = (int) std::max<size_t>(148 * 4, (n_src + (size_t) kGicpThreads * 16 - 1) / ((size_t) kGicpThreads * 16));
+        if ((size_t) n_blocks > partial_blocks) {
+            if (d_partial) WCU_CHECK(cudaFree(d_partial));
+            d_partial = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(long long) * kCostVals * (size_t) n_blocks));
+            partial_blocks = (size_t) n_blocks;
+        }
+        {   // fixed-point exponent of the cost sums from the source extent (oracle: gicp_sum_exponent)
+            unsigned bb[6];
+            WCU_CHECK(cudaMemcpyAsync(bb, src.cloud.d_bbox, sizeof bb, cudaMemcpyDeviceToHost, stream));
+            WCU_CHECK(cudaStreamSynchronize(stream));
+            double bmax = 0;
+            for (int d = 0; d < 6; ++d) {
+                const unsigned u = bb[d];
+                const unsigned bits = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;   // ordered_to_float
+                float v;
+                std::memcpy(&v, &bits, sizeof v);
+                if (std::isfinite(v)) bmax = std::max(bmax, (double) std::fabs(v));
+            }
+            int e;
+            std::frexp(std::max(bmax, 64.0) * 32768.0, &e);
+            sum_k = 50 - e;
+        }
         WCU_CHECK(cudaMemsetAsync(d_pos, 0xff, n_src * sizeof(int), stream));
         const double dist_threshold = 5.0 * 5.0;  // corr_dist_threshold_ (libwave never sets it)
         float thr = (float) dist_threshold;

@@ -28,6 +28,7 @@ struct SetupArgs {
     Acc128 *acc;
     double max_corr;
     int *fb_count;
+    unsigned *ticket;
 };
 
 __device__ double bbox_max_abs(const unsigned *bb) {
@@ -49,6 +50,7 @@ __global__ void setup_kernel(SetupArgs a) {
     }
     if (t != 0) return;
     if (a.fb_count) *a.fb_count = 0;
+    if (a.ticket) *a.ticket = 0u;
     MatchConsts &mc = *a.mc;
     for (int d = 0; d < 3; ++d) {
         mc.src_lo[d] = ordered_to_float(a.src_bbox[d]);
@@ -159,6 +161,8 @@ struct IcpHandle {
     int trace_cap = 0;
     // tiled correspondence kernel (tile_nn.cuh): queries it hands to the LBVH walk
     bool use_tile = false;
+    bool use_fused = true;    // one launch per iteration (iterate_kernel); WAVECU_FUSED=0: correspond / reduce / solve
+    unsigned *d_ticket = nullptr;
     int *d_fb_count = nullptr, *d_fb_list = nullptr;
 
     // pinned host mirrors
@@ -240,8 +244,11 @@ int IcpHandle::init() {
     tgt.want_boxes = use_tile;
     WCU_CHECK(cudaFuncSetAttribute(correspond_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int) sizeof(TileSmem)));
+    if (const char *e = getenv("WAVECU_FUSED")) use_fused = atoi(e) != 0;   // tuning knob
     WCU_CHECK(cudaMalloc((void **) &d_fb_count, sizeof(int)));
     WCU_CHECK(cudaMemset(d_fb_count, 0, sizeof(int)));
+    WCU_CHECK(cudaMalloc((void **) &d_ticket, sizeof(unsigned)));
+    WCU_CHECK(cudaMemset(d_ticket, 0, sizeof(unsigned)));
     src.device = tgt.cloud.device = device;
     src.stream = aux;
     tgt.cloud.stream = stream;
@@ -455,7 +462,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         fill_int_kernel<<<(unsigned) ((n_src + 255) / 256), 256, 0, stream>>>(d_nn_pos, -1, n_src);
         ++extra_launches;
     }
-    SetupArgs sa{src.d_bbox, tgt.cloud.d_bbox, d_mc, d_st, d_acc, prm.max_corr, d_fb_count};
+    SetupArgs sa{src.d_bbox, tgt.cloud.d_bbox, d_mc, d_st, d_acc, prm.max_corr, d_fb_count, d_ticket};
     setup_kernel<<<1, 256, 0, stream>>>(sa);
     ++extra_launches;
     WCU_CHECK(cudaGetLastError());
@@ -486,17 +493,31 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     const unsigned grid_red = (unsigned) std::max<size_t>(1, (n_src + kReduceThreads - 1) / kReduceThreads);
     std::vector<cudaEvent_t> it_ev;
     int launched = 0;
+    long long launches_total = 0;
     bool finished = (n_src == 0 || n_tgt == 0);  // initCompute fails -> converged_ = false
     for (int k = 0; !finished && k < max_iter; ++k) {
         if (profiling) {
             it_ev.push_back(next_event());
             WCU_CHECK(cudaEventRecord(it_ev.back(), stream));
         }
-        if (tiled) {
+        so.launch = k + 1;
+        // one launch per iteration, except while the caller's normals are still on their way (they are
+        // gathered behind the first search) and with the tiled search (its own kernel pair)
+        const bool fused = use_fused && !tiled && !late_normals;
+        if (fused) {
+            const FusedArgs fa{ia, so, d_ticket};
+            if (prm.estimator == WAVECU_EST_POINT_TO_PLANE)
+                iterate_kernel<WAVECU_EST_POINT_TO_PLANE><<<grid_nn, kIterThreads, 0, stream>>>(fa);
+            else
+                iterate_kernel<WAVECU_EST_SVD><<<grid_nn, kIterThreads, 0, stream>>>(fa);
+            launches_total += 1;
+        } else if (tiled) {
             correspond_tile_kernel<<<grid_tile, kTileQ, sizeof(TileSmem), stream>>>(ia, tgt.boxes, fb);
             tile_fallback_kernel<<<grid_fb, kIterThreads, 0, stream>>>(ia, fb);
+            launches_total += 4;
         } else {
             correspond_kernel<<<grid_nn, kIterThreads, 0, stream>>>(ia);
+            launches_total += 3;
         }
         if (profiling) {
             it_ev.push_back(next_event());
@@ -507,13 +528,14 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             rc = tgt.sort_normals();
             if (rc) return rc;
         }
-        so.launch = k + 1;
-        if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
-            reduce_kernel<WAVECU_EST_POINT_TO_PLANE><<<grid_red, kReduceThreads, 0, stream>>>(ia);
-            solve_kernel<WAVECU_EST_POINT_TO_PLANE><<<1, 64, 0, stream>>>(so);
-        } else {
-            reduce_kernel<WAVECU_EST_SVD><<<grid_red, kReduceThreads, 0, stream>>>(ia);
-            solve_kernel<WAVECU_EST_SVD><<<1, 64, 0, stream>>>(so);
+        if (!fused) {
+            if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
+                reduce_kernel<WAVECU_EST_POINT_TO_PLANE><<<grid_red, kReduceThreads, 0, stream>>>(ia);
+                solve_kernel<WAVECU_EST_POINT_TO_PLANE><<<1, 64, 0, stream>>>(so);
+            } else {
+                reduce_kernel<WAVECU_EST_SVD><<<grid_red, kReduceThreads, 0, stream>>>(ia);
+                solve_kernel<WAVECU_EST_SVD><<<1, 64, 0, stream>>>(so);
+            }
         }
         if (profiling) {
             it_ev.push_back(next_event());
@@ -565,7 +587,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     result_n_src = n_src;
 
     stats.iterate_launches = last.iter;
-    stats.kernel_launches = (src.launches + tgt.cloud.launches - launches0) + extra_launches + (tiled ? 4LL : 3LL) * launched;
+    stats.kernel_launches = (src.launches + tgt.cloud.launches - launches0) + extra_launches + launches_total;
     stats.pairs = (long long) last.iter * (long long) n_src;
     stats.fallback_queries = last.fb_total;
     if (profiling) {
@@ -1071,7 +1093,7 @@ void IcpHandle::release() {
     tgt.release();
     for (void *p : {(void *) d_nn_pos, (void *) d_nn_idx, (void *) d_nn_d2, (void *) d_out_idx, (void *) d_out_d2,
                     (void *) d_aligned, (void *) d_mc, (void *) d_st, (void *) d_acc, (void *) d_trace,
-                    (void *) d_fb_count, (void *) d_fb_list})
+                    (void *) d_fb_count, (void *) d_fb_list, (void *) d_ticket})
         if (p) cudaFree(p);
     vox.release();
     for (void *p : {(void *) d_orig_src, (void *) d_orig_tgt, (void *) d_pos2})

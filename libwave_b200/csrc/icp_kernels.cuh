@@ -136,24 +136,21 @@ __global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) correspond_kernel
 // Warp totals go to shared memory, block totals to a few 64-bit global atomics.
 __device__ __forceinline__ long long fix_term(double v, double scale) { return __double2ll_rn(v * scale); }
 
+// Block-level body shared by reduce_kernel and the fused iteration kernel: the calling thread's pair
+// (if any) is its moved source point c, its match at sorted position pos and their fp32 distance.
 template <int EST>
-__global__ void __launch_bounds__(kReduceThreads) reduce_kernel(IterArgs a) {
+__device__ __forceinline__ void reduce_block(const IterArgs &a, bool pair, const float4 &c, int pos, float d2f,
+                                             unsigned long long *s_acc /* shared, NV + 1 */) {
     constexpr int NV = EstTraits<EST>::NV;
-    if (a.st->done) return;
-    __shared__ unsigned long long s_acc[NV + 1];
     if (threadIdx.x <= NV) s_acc[threadIdx.x] = 0ull;
     __syncthreads();
     const double s_lin = a.mc->s_lin, s_quad = a.mc->s_quad, s_d2 = a.mc->s_d2, s_plane = a.mc->s_plane;
-    const int s = blockIdx.x * kReduceThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int pos = (s < a.n_src) ? a.nn_pos[s] : -1;
-    const bool pair = pos >= 0;
     double in[7] = {0, 0, 0, 0, 0, 0, 0};  // SVD: p, q.  PLANE: J[0..5], d
     double d2 = 0.0;
     bool plane_ok = false;
     if (pair) {
-        const float4 c = a.cur[s];
-        d2 = (double) a.nn_d2[s];
+        d2 = (double) d2f;
         const float4 q = __ldg(a.tgt + pos);
         if (EST == WAVECU_EST_SVD) {
             in[0] = c.x; in[1] = c.y; in[2] = c.z;
@@ -216,6 +213,21 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_kernel(IterArgs a) {
             atomic_add128(dst, (unsigned long long) tot, tot < 0 ? -1LL : 0LL);
         }
     }
+}
+
+template <int EST>
+__global__ void __launch_bounds__(kReduceThreads) reduce_kernel(IterArgs a) {
+    if (a.st->done) return;
+    __shared__ unsigned long long s_acc[EstTraits<EST>::NV + 1];
+    const int s = blockIdx.x * kReduceThreads + threadIdx.x;
+    const int pos = (s < a.n_src) ? a.nn_pos[s] : -1;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    float d2 = 0.0f;
+    if (pos >= 0) {
+        c = a.cur[s];
+        d2 = a.nn_d2[s];
+    }
+    reduce_block<EST>(a, pos >= 0, c, pos, d2, s_acc);
 }
 
 struct SolveArgs {
@@ -344,13 +356,12 @@ __device__ inline bool solve6(const double A_in[36], const double b_in[6], doubl
     return true;
 }
 
+// Estimator + convergence test for the calling block (>= 33 threads): used by solve_kernel, and by the
+// last block of the fused iteration kernel, which reads the accumulators other blocks just added to
+// (hence the L1-bypassing loads).
 template <int EST>
-__global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
+__device__ __noinline__ void solve_block(const SolveArgs &a) {
     constexpr int NV = EstTraits<EST>::NV;
-    if (a.st->done) {
-        if (threadIdx.x == 0) publish_progress(a, 1);
-        return;
-    }
     // threads 0..NV: one accumulator each, summed over the slots (and cleared for the next
     // iteration); then thread 0 runs the estimator
     __shared__ unsigned long long s_lo[NV + 1];
@@ -361,7 +372,9 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
 #pragma unroll 4
         for (int sl = 0; sl < kAccSlots; ++sl) {
             Acc128 &c = a.acc[sl * kMaxAcc + threadIdx.x];
-            t += ((__int128) c.hi << 64) + (__int128) c.lo;
+            const unsigned long long lo = __ldcg(&c.lo);
+            const long long hi = __ldcg(&c.hi);
+            t += ((__int128) hi << 64) + (__int128) lo;
             c.lo = 0;
             c.hi = 0;
         }
@@ -501,6 +514,82 @@ __global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
         st.done = 1;
     }
     publish_progress(a, conv);
+}
+
+template <int EST>
+__global__ void __launch_bounds__(64) solve_kernel(SolveArgs a) {
+    if (a.st->done) {
+        if (threadIdx.x == 0) publish_progress(a, 1);
+        return;
+    }
+    solve_block<EST>(a);
+}
+
+// One ICP iteration in one launch: correspond_kernel's search, the estimator reduction of the pair it
+// just found (no second pass over the cloud), and - in whichever block finishes last - the estimator
+// and convergence test.  Blocks order their accumulator updates before their ticket with a fence; the
+// last block resets the ticket for the next launch.
+struct FusedArgs {
+    IterArgs it;
+    SolveArgs so;
+    unsigned *ticket;
+};
+
+template <int EST>
+__global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) iterate_kernel(const __grid_constant__ FusedArgs f) {
+    const IterArgs &a = f.it;
+    if (a.st->done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) publish_progress(f.so, 1);
+        return;
+    }
+    __shared__ float sT[12];
+    __shared__ unsigned long long s_acc[EstTraits<EST>::NV + 1];
+    __shared__ bool s_last;
+    if (threadIdx.x < 12) sT[threadIdx.x] = a.st->T_inc[threadIdx.x];
+    __syncthreads();
+    const int s = blockIdx.x * kIterThreads + threadIdx.x;
+    float4 moved = make_float4(0.f, 0.f, 0.f, 0.f);
+    float best = a.mc->thr;
+    int best_idx = 0x7fffffff, best_pos = -1;
+    if (s < a.n_src) {
+        const float4 c = a.cur[s];
+        if (finite3(c.x, c.y, c.z)) {
+            moved = make_float4(xform_row(sT + 0, c.x, c.y, c.z), xform_row(sT + 4, c.x, c.y, c.z),
+                                xform_row(sT + 8, c.x, c.y, c.z), c.w);
+            a.cur[s] = moved;
+            const int warm = a.nn_pos[s];
+            if (warm >= 0) {
+                const float4 p = __ldg(a.tgt + warm);
+                const float d = l2_simple(moved.x, moved.y, moved.z, p.x, p.y, p.z);
+                if (d <= best) {
+                    best = d;
+                    best_idx = __float_as_int(p.w);
+                    best_pos = warm;
+                }
+            }
+#if WCU_LEAF == 1
+            nn_search_cells(moved.x, moved.y, moved.z, a.ix, best, best_idx, best_pos);
+#else
+            nn_search(moved.x, moved.y, moved.z, a.ix, best, best_idx, best_pos);
+#endif
+            a.nn_pos[s] = best_pos;
+            a.nn_idx[s] = best_pos >= 0 ? best_idx : -1;
+            a.nn_d2[s] = best;
+        } else {  // pads and non-finite source points take no part
+            a.nn_pos[s] = -1;
+            a.nn_idx[s] = -1;
+            a.nn_d2[s] = INFINITY;
+        }
+    }
+    reduce_block<EST>(a, best_pos >= 0, moved, best_pos, best, s_acc);
+    __threadfence();   // this block's accumulator updates (and match arrays) before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(f.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *f.ticket = 0u;
+    solve_block<EST>(f.so);
 }
 
 }  // namespace wavecu

@@ -25,6 +25,7 @@
 #include <limits>
 
 #include "kdtree.hpp"
+#include "smallmat.hpp"
 
 namespace wo {
 
@@ -63,8 +64,11 @@ void eig_sym3_desc(const double A_in[9], double evals[3], double V[9]) {  // eig
                 }
             }
     }
-    int order[3] = {0, 1, 2};
-    std::sort(order, order + 3, [&](int a, int b) { return std::fabs(A[a][a]) > std::fabs(A[b][b]); });
+    int o0 = 0, o1 = 1, o2 = 2;  // stable sort by descending |eigenvalue| (fixed compare-exchange order)
+    if (std::fabs(A[o1][o1]) > std::fabs(A[o0][o0])) std::swap(o0, o1);
+    if (std::fabs(A[o2][o2]) > std::fabs(A[o1][o1])) std::swap(o1, o2);
+    if (std::fabs(A[o1][o1]) > std::fabs(A[o0][o0])) std::swap(o0, o1);
+    const int order[3] = {o0, o1, o2};
     for (int j = 0; j < 3; ++j) {
         evals[j] = A[order[j]][order[j]];
         for (int i = 0; i < 3; ++i) V[3 * i + j] = Q[i][order[j]];
@@ -177,7 +181,40 @@ struct Problem {  // the OptimizationFunctorWithIndices state
     const std::vector<double> *mahal;  // per source index, 9 doubles
     float base[16];                    // base_transformation_ = guess = identity
     long long evals = 0;
+    int k = 28;                        // fixed-point exponent of the cost sums (gicp_sum_exponent)
 };
+
+// The 13 sums of fdf are accumulated exactly: every term t is rounded once to an integer multiple of
+// 2^-k (clamped to +-2^52 units so that absurd trial poses cannot overflow) and added in 128-bit
+// integers - the same spec as the ICP estimator sums.  The result does not depend on the
+// order of the pairs, which is what lets the device (Morton order, blocks, warps) and this loop (cloud
+// order) drive pcl::BFGS through the same trajectory.  PCL itself adds the terms sequentially in fp64;
+// the difference is ~1e-12 relative, far below what moves the optimiser, but any difference at all
+// can flip a line-search decision - the two implementations must not differ.
+// k: terms are bounded by max(|p|, 64 m) * 2^15 (|M| <= 500 from the regularised covariances, residuals
+// of trial poses taken as < 64 m).
+int gicp_sum_exponent(const float *src, size_t n) {
+    double bmax = 0;
+    for (size_t i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d) {
+            const float v = src[4 * i + d];
+            if (std::isfinite(v)) bmax = std::max(bmax, (double) std::fabs(v));
+        }
+    int e;
+    std::frexp(std::max(bmax, 64.0) * 32768.0, &e);
+    return 50 - e;
+}
+
+inline void fix_add(__int128 &acc, double term, double scale) {
+    double v = term * scale;
+    v = std::fmin(std::fmax(v, -4503599627370496.0), 4503599627370496.0);
+    acc += (__int128) std::llrint(v);
+}
+inline double fix_value(__int128 v, int k) {
+    Fix128 f;
+    f.v = v;
+    return f.value(k);
+}
 
 // computeRDerivative as written (matricesInnerProd(m1, m2) = sum_ij m1(j,i) * m2(i,j))
 void r_derivative(const double x[6], const double R[9], double g[6]) {
@@ -229,7 +266,8 @@ void fdf(Problem &P, const double x[6], double *f_out, double *g /*nullable*/) {
     float T[16];
     std::memcpy(T, P.base, sizeof T);
     apply_state(T, x);
-    double f = 0, gt[3] = {0, 0, 0}, R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    __int128 sf = 0, sg[3] = {0, 0, 0}, sR[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const double scale = std::ldexp(1.0, P.k);
     const int m = (int) P.is->size();
     for (int i = 0; i < m; ++i) {
         const float *ps = P.src + 4 * (size_t) (*P.is)[(size_t) i];
@@ -240,15 +278,19 @@ void fdf(Problem &P, const double x[6], double *f_out, double *g /*nullable*/) {
         const double *M = P.mahal->data() + 9 * (size_t) (*P.is)[(size_t) i];
         const double temp[3] = {M[0] * res[0] + M[1] * res[1] + M[2] * res[2], M[3] * res[0] + M[4] * res[1] + M[5] * res[2],
                                 M[6] * res[0] + M[7] * res[1] + M[8] * res[2]};
-        f += res[0] * temp[0] + res[1] * temp[1] + res[2] * temp[2];
+        fix_add(sf, res[0] * temp[0] + res[1] * temp[1] + res[2] * temp[2], scale);
         if (g) {
-            for (int d = 0; d < 3; ++d) gt[d] += temp[d];
+            for (int d = 0; d < 3; ++d) fix_add(sg[d], temp[d], scale);
             float pb[3];
             xform4(P.base, ps, pb);
             for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) R[3 * r + c] += (double) pb[r] * temp[c];
+                for (int c = 0; c < 3; ++c) fix_add(sR[3 * r + c], (double) pb[r] * temp[c], scale);
         }
     }
+    const double f = fix_value(sf, P.k);
+    double gt[3], R[9];
+    for (int d = 0; d < 3; ++d) gt[d] = fix_value(sg[d], P.k);
+    for (int q = 0; q < 9; ++q) R[q] = fix_value(sR[q], P.k);
     if (f_out) *f_out = f / m;
     if (g) {
         for (int d = 0; d < 3; ++d) g[d] = gt[d] * (2.0 / m);
@@ -625,6 +667,7 @@ void gicp_align(const float *source, size_t n_src, const float *target, size_t n
         P.it = &it;
         P.mahal = &mahal;
         identity4(P.base);
+        P.k = gicp_sum_exponent(source, n_src);
         Bfgs bfgs(P);
         bfgs.init(x);
         int inner = 0, result = kRunning;

@@ -183,6 +183,26 @@ def test_gicp_500k_recovers_rigid_copy(W, synth):
     assert rot_angle(T[:3, :3], synth.T_TRUE[:3, :3]) < 1e-4
 
 
+def test_gicp_500k_noisy_pair_equals_oracle(W, oracle, synth):
+    """BASELINE config 3 at its own size and on the bench's own inputs (two noisy 500 k-point scans):
+    the GPU follows the oracle's BFGS trajectory exactly - outer iterations, cost evaluations,
+    correspondences and the final transform, bit for bit (exact sums on both sides; the oracle needs
+    ~25 s for this case).  How close that transform is to the truth is PCL GICP's own property: with
+    k = 10 neighbours on a 7813-step ring every neighbourhood is a line segment, the plane-to-plane
+    model degenerates, and the restated algorithm stops 16 cm from the truth (1.6 cm / 0.6 cm at
+    10 k / 200 k points) - recorded here, not asserted away."""
+    src, tgt = synth.scan_pair(500_000)
+    m = W.GICPMatcher(W.GICPMatcherParams(res=-1))
+    m.setup(src, tgt)
+    ok = m.match()
+    ref = oracle.gicp_align(src, tgt)
+    st = m.stats()
+    assert ok == ref.converged and m.iterations == ref.iterations
+    assert st["evaluations"] == ref.evaluations and st["n_corr"] == ref.n_corr
+    assert np.array_equal(m.getResult().astype(np.float32), ref.T)
+    assert np.abs(m.getResult()[:3, 3] - synth.T_TRUE[:3, 3]).max() < 0.25
+
+
 def test_ndt_1m_vs_5m_score_prefers_true_pose(W, synth, scan_1m):
     """BASELINE config 4: 1M-point scan against the 5M-point map, 0.5 m voxels."""
     from test_gpu_ndt import pose_matrix
