@@ -1,29 +1,35 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the registration hot path (BASELINE.json metric).
+"""bench.py - benchmarks of the registration hot path (BASELINE.json metric and configs).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload icp1m|batch256|gicp500k|ndt1m5m] [--skip-cpu] [--no-batch]
 
-One "step" = one ICPMatcher::match() (point-to-plane estimator, full resolution, reference
-default parameters) of a 1 M-point synthetic Velodyne-style scan against a 1 M-point scan of the
-same scene (BASELINE.json configs[1]; generator: libwave_b200/synth.py), search
-structure build included.  Metric: point-pairs/s = sum over ICP iterations of source points queried
-/ time.  N > 1: the batch-of-scans case - every rank matches its own scan pair (weak scaling), no
-data-path collective, one NCCL all-gather of the 4x4 results per step.
+icp1m (default, the headline; BASELINE.json configs[1]).  One "step" = one ICPMatcher::match()
+(point-to-plane estimator, full resolution, reference default parameters) of a 1 M-point synthetic
+Velodyne-style scan against a 1 M-point scan of the same scene (generator: libwave_b200/synth.py,
+SURVEY.md 8(d)), search-structure build included.  Metric: point-pairs/s = sum over ICP iterations of
+source points queried / time.  N > 1: the batch-of-scans case - every rank matches its own scan pair
+(weak scaling), no data-path collective, results gathered once after the timed steps.  The line also
+carries a `batch256` sub-record (configs[4]: 256 independent 200 k-point scan-to-map alignments sharded
+over the ranks through the C batch API, map indexed once per GPU, one all-gather of the records).
 
 `value`    inputs already resident in HBM, timed with CUDA events on the launch stream.
 `e2e`      the same match through the public host API from pinned host clouds (H2D copies and the
            result read-back inside the timed region).
-`roofline` the fused correspondence kernel: algorithmic bytes per launch / mean launch time
-           (CUDA events around every launch, inside the timed region) against the measured HBM
-           copy bandwidth in MEASURED_PEAKS.json.
+`roofline` the dominant kernel (icp1m: iterate_kernel - transform + exact 1-NN + estimator reduction
+           in one launch per iteration): algorithmic bytes per launch / mean launch time (CUDA events
+           around every launch, inside the timed region) against the measured HBM copy bandwidth in
+           MEASURED_PEAKS.json.
+`parity`   the GPU result of this very workload compared with the CPU oracle outside the timed region.
 `cpu_baseline` / --impl reference: the CPU oracle (restated PCL path; the real PCL cannot be built
            here) on the host cores, MultiMatcher-style: one single-threaded
-           match per hardware thread, each capped at a few iterations (bounded sample).
+           match per hardware thread on a bounded sample of the workload.
+gicp500k / ndt1m5m: BASELINE.json configs[2] / configs[3] with the same keys; one "pair" there is one
+           (source point, cost / derivative evaluation), SURVEY.md 8(d).
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import pathlib
@@ -45,22 +51,57 @@ UNIT = "point-pairs/s"
 L2_FLUSH_BYTES = 256 << 20
 
 
-def make_workload(rank: int):
-    from libwave_b200 import synth
-    src, tgt, nrm = synth.scan_pair(N_POINTS, scan_id=None if rank == 0 else rank, return_normals=True)
-    return synth.to_xyzw(src), synth.to_xyzw(tgt), synth.to_xyzw(nrm)
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
-def workload_config(n_gpus: int) -> dict:
-    return {
-        "workload": "ICPMatcher point-to-plane, 1M-point synthetic Velodyne-style scan vs 1M-point scan of the "
-                    "same scene, res=-1 (full resolution), max_corr=3, max_iter=100, t_eps=1e-8, fit_eps=1e-2",
-        "n_source": N_POINTS, "n_target": N_POINTS, "estimator": "point_to_plane_lls",
-        "normals": "analytic surface normals from the generator, uploaded with the target",
-        "parallelism": f"batch-of-scans x{n_gpus} (one independent scan pair per GPU)",
-        "l2": "flushed between timed steps (256 MiB write); inside a step the clouds are re-read every ICP "
-              "iteration by design",
-    }
+def pin_to_gpu_numa_node(gpu_index: int) -> str:
+    """Best effort: run this rank (and allocate its page-locked buffers) on the host cores of its GPU's
+    NUMA node, so that 8 ranks do not push their uploads through one socket's memory."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not bus:
+            return "unknown"
+        dom, rest = bus.split(":", 1)
+        node = int(pathlib.Path(f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node").read_text())
+        if node < 0:
+            return "single node"
+        cpus = []
+        for part in pathlib.Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"node {node} ({len(allowed)} cpus)"
+        return f"node {node} (not in this process's cpu set)"
+    except Exception as e:  # noqa: BLE001 - placement is an optimisation, never a failure
+        return f"unavailable ({type(e).__name__})"
+
+
+def peak_hbm():
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        return float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_of(kernel_key: str):
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        return json.loads(tpath.read_text()).get(kernel_key)
+    return None
+
+
+def pose_error(T, T_true):
+    T, T_true = np.asarray(T, dtype=np.float64), np.asarray(T_true, dtype=np.float64)
+    dt = float(np.abs(T[:3, 3] - T_true[:3, 3]).max())
+    d = np.linalg.norm(T[:3, :3] - T_true[:3, :3])
+    return dt, float(2.0 * np.arcsin(min(1.0, d / (2.0 * np.sqrt(2.0)))))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -117,43 +158,100 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(src, tgt, nrm, threads: int):
-    """The oracle's PCL-faithful ICP on the host cores, MultiMatcher-style (one single-threaded match
-    per hardware thread, multi_matcher.hpp:32).  Returns (pairs_per_s, description, seconds)."""
-    from oracle import oracle as O
-    O.build()
-    O.lib()
-    done = [0] * threads
+def run_threads(fn, threads: int):
+    """fn(k) on `threads` host threads at once (MultiMatcher-style); returns (results, wall seconds)."""
+    out = [None] * threads
 
     def work(k):
-        r = O.icp_align(src, tgt, estimator=O.EST_POINT_TO_PLANE, sum_mode=O.SUM_PCL, target_normals=nrm,
-                        max_iter=CPU_SAMPLE_ITERS, nn_threads=1)
-        done[k] = r.iterations * src.shape[0]
-
+        out[k] = fn(k)
     t0 = time.perf_counter()
     th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
     for t in th:
         t.start()
     for t in th:
         t.join()
-    dt = time.perf_counter() - t0
+    return out, time.perf_counter() - t0
+
+
+# ================================================================================================
+# icp1m
+# ================================================================================================
+def make_workload(rank: int):
+    from libwave_b200 import synth
+    src, tgt, nrm = synth.scan_pair(N_POINTS, scan_id=None if rank == 0 else rank, return_normals=True)
+    return synth.to_xyzw(src), synth.to_xyzw(tgt), synth.to_xyzw(nrm)
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": "ICPMatcher point-to-plane, 1M-point synthetic Velodyne-style scan vs 1M-point scan of the "
+                    "same scene, res=-1 (full resolution), max_corr=3, max_iter=100, t_eps=1e-8, fit_eps=1e-2",
+        "n_source": N_POINTS, "n_target": N_POINTS, "estimator": "point_to_plane_lls",
+        "normals": "analytic surface normals from the generator, uploaded with the target",
+        "parallelism": f"batch-of-scans x{n_gpus} (one independent scan pair per GPU)",
+        "l2": "flushed between timed steps (256 MiB write); inside a step the clouds are re-read every ICP "
+              "iteration by design",
+        "cpu_arm": "one single-threaded oracle match per hardware thread, all at once (MultiMatcher's structure, "
+                   "multi_matcher.hpp:32) - conservative against BASELINE.md's 1-thread plan for single-match "
+                   "configs; `cores` says how many",
+    }
+
+
+def cpu_reference_sample(src, tgt, nrm, threads: int):
+    """The oracle's PCL-faithful ICP on the host cores, MultiMatcher-style (one single-threaded match
+    per hardware thread, multi_matcher.hpp:32).  Returns (pairs_per_s, description, seconds)."""
+    from oracle import oracle as O
+    O.build()
+    O.lib()
+
+    def work(_):
+        r = O.icp_align(src, tgt, estimator=O.EST_POINT_TO_PLANE, sum_mode=O.SUM_PCL, target_normals=nrm,
+                        max_iter=CPU_SAMPLE_ITERS, nn_threads=1)
+        return r.iterations * src.shape[0]
+    done, dt = run_threads(work, threads)
     sample = (f"{threads} concurrent single-threaded matches of the same 1M/1M pair (MultiMatcher-style), each "
               f"capped at {CPU_SAMPLE_ITERS} ICP iterations, kd-tree build included; {dt:.1f} s wall")
     return sum(done) / dt, sample, dt
 
 
-def host_threads() -> int:
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return max(1, os.cpu_count() or 1)
+def icp_parity(m, src, tgt, nrm, threads: int) -> dict:
+    """The GPU result of the bench workload against the CPU oracle, outside the timed region."""
+    from oracle import oracle as O
+    from libwave_b200 import synth
+    ref = O.icp_align(src, tgt, estimator=O.EST_POINT_TO_PLANE, sum_mode=O.SUM_EXACT, target_normals=nrm,
+                      nn_threads=threads)
+    pcl = O.icp_align(src, tgt, estimator=O.EST_POINT_TO_PLANE, sum_mode=O.SUM_PCL, target_normals=nrm,
+                      nn_threads=threads)
+    q, mm, d2 = m.correspondences()
+    mse, ncorr, _ = m.trace()
+    T = m.getResult()
+    dt_pcl, dr_pcl = pose_error(T, pcl.T)
+    dt_true, dr_true = pose_error(T, synth.T_TRUE)
+    return {
+        "oracle": "oracle.icp_align on the same clouds (restated PCL; exact-sum mode for equality, PCL-faithful "
+                  "summation mode for the tolerance)",
+        "iterations": int(m.iterations), "oracle_iterations": int(ref.iterations),
+        "iterations_equal": bool(m.iterations == ref.iterations == pcl.iterations),
+        "n_correspondences": int(len(q)),
+        "correspondence_indices_equal": bool(np.array_equal(q, ref.corr_query) and np.array_equal(mm, ref.corr_match)),
+        "correspondence_distances_equal": bool(np.array_equal(d2, ref.corr_dist)),
+        "mse_trace_equal": bool(np.array_equal(mse, ref.mse) and np.array_equal(ncorr, ref.n_corr)),
+        "max_abs_T_diff_vs_exact_sum_oracle": float(np.abs(T - ref.T.astype(np.float64)).max()),
+        "vs_pcl_summation_oracle": {"translation_m": dt_pcl, "rotation_rad": dr_pcl,
+                                    "within_1e-4m_1e-5rad": bool(dt_pcl < 1e-4 and dr_pcl < 1e-5)},
+        "vs_ground_truth": {"translation_error_m": dt_true, "rotation_error_rad": dr_true,
+                            "note": "2 cm range noise; PCL's relative-MSE rule stops after 4 iterations"},
+    }
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.workload == "gicp500k":
+        return run_reference_gicp(args)
+    if args.workload == "ndt1m5m":
+        return run_reference_ndt(args)
     src, tgt, nrm = make_workload(0)
     threads = host_threads()
     vals, secs = [], []
@@ -179,26 +277,43 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def init_dist():
     import torch
     import torch.distributed as dist
-
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    numa = pin_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    return torch, dist, rank, local_rank, world, dev, numa
 
+
+def run_ours(args):
+    torch, dist, rank, local_rank, world, dev, numa = init_dist()
     import libwave_b200 as W
     from libwave_b200 import batch
 
     if args.workload == "batch256":
-        return run_batch(args, W, batch, torch, dist, rank, local_rank, world, dev)
+        rec = batch256(args, W, batch, torch, dist, rank, local_rank, world, dev)
+        if rank == 0:
+            print(json.dumps(rec))
+        finish_dist(dist, world)
+        return 0
+    if args.workload == "gicp500k":
+        rc = run_gicp(args, W, batch, torch, dist, rank, local_rank, world, dev)
+        finish_dist(dist, world)
+        return rc
+    if args.workload == "ndt1m5m":
+        rc = run_ndt(args, W, batch, torch, dist, rank, local_rank, world, dev)
+        finish_dist(dist, world)
+        return rc
+
     src, tgt, nrm = make_workload(rank)
     n = src.shape[0]
     # the matcher launches on this stream, and the timing events below are recorded on it
@@ -210,35 +325,18 @@ def run_ours(args):
     d_src, d_tgt, d_nrm = (torch.from_numpy(a).to(dev) for a in (src, tgt, nrm))
     h_src, h_tgt, h_nrm = (torch.from_numpy(a).pin_memory() for a in (src, tgt, nrm))
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    result_buf = torch.zeros(18, dtype=torch.float64, device=dev)
-    gathered = torch.zeros(world * 18, dtype=torch.float64, device=dev) if world > 1 else None
-    h_result = torch.zeros(18, dtype=torch.float64).pin_memory()
-
-    def share_result(ok):
-        # every rank ends a step holding every rank's {T, converged, iterations}: one pinned H2D copy and one
-        # NCCL all-gather of 144 B per rank
-        h_result[:16] = torch.from_numpy(m.getResult().reshape(16))
-        h_result[16], h_result[17] = float(ok), float(m.iterations)
-        result_buf.copy_(h_result, non_blocking=True)
-        dist.all_gather_into_tensor(gathered, result_buf)
 
     def step_device():
         m.setRefDevice(d_src.data_ptr(), n)
         m.setTargetDevice(d_tgt.data_ptr(), n)
         m.setTargetNormalsDevice(d_nrm.data_ptr(), n)
-        ok = m.match()
-        if world > 1:
-            share_result(ok)
-        return ok
+        return m.match()
 
     def step_host():
         m.setRef(h_src.numpy())
         m.setTarget(h_tgt.numpy())
         m.setTargetNormals(h_nrm.numpy())
-        ok = m.match()  # the 4x4 result, flags and trace are read back to the host inside match()
-        if world > 1:
-            share_result(ok)
-        return ok
+        return m.match()  # the 4x4 result, flags and trace are read back to the host inside match()
 
     def barrier():
         if world > 1:
@@ -288,122 +386,425 @@ def run_ours(args):
     clocks = sampler.finish() if sampler else None
     m.set_profiling(False)
 
+    # every rank ends holding every rank's {T, converged, iterations}: ONE gather, after the timed steps
+    ok = step_device()
+    local = {rank: batch.pack_record(m.getResult(), ok, m.iterations)}
+    table = batch.gather_records(local, world, device=dev)
+
+    sub = None
+    if not args.no_batch:
+        sub = batch256(args, W, batch, torch, dist, rank, local_rank, world, dev, steps=max(1, min(args.steps, 3)))
+
     if rank == 0:
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # algorithmic bytes per launch of the NN-correspondence kernel:
-        # 16 B query + 8 B result (int32 index + fp32 d2) per source point, 16 B per target point.
-        # (The kernel also writes the moved working cloud back, 16 B/point, which is not counted.)
-        alg_bytes = 24.0 * n + 16.0 * n
+        peak, peak_src = peak_hbm()
+        # Algorithmic bytes per launch of the fused iteration kernel ("fused ICP iteration,
+        # parity mode" + the point-to-plane normals): the working cloud read and rewritten (16 + 16 B per source
+        # point: PCL transforms it in place every iteration), every target point and its normal once (16 + 16 B).
+        # The search alone (row A4) is 24 N_src + 16 N_tgt = 40 MB.
+        alg_bytes = 32.0 * n + 32.0 * n
         mean_launch_ms = prof_run["iterate_ms"] / max(1, prof_run["iterate_launches"])
         achieved = alg_bytes / (mean_launch_ms * 1e-3) / 1e9 if mean_launch_ms > 0 else 0.0
-        traffic = None
-        tpath = ROOT / "profiles" / "traffic.json"
-        if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get("correspond_kernel_dram_bytes_per_launch")
+        threads = host_threads()
         if args.skip_cpu:
-            cpu_v, cpu_sample = None, "skipped (--skip-cpu, profiling run)"
+            cpu_v, cpu_sample, parity = None, "skipped (--skip-cpu, profiling run)", None
         else:
-            cpu_v, cpu_sample, _ = cpu_reference_sample(src, tgt, nrm, host_threads())
+            cpu_v, cpu_sample, _ = cpu_reference_sample(src, tgt, nrm, threads)
+            step_device()
+            parity = icp_parity(m, src, tgt, nrm, threads)
+        cfg = workload_config(world)
+        cfg["numa"] = numa
         line = {
             "metric": METRIC, "value": dev_run["pairs_all"] / (dev_run["total_ms"] * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_run["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_run["pairs_all"] / (e2e_run["total_ms"] * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(3 * 16 * n), "d2h_bytes_per_step": int(256 + 80 * dev_run["iters"]),
                     "ms_per_step": e2e_run["total_ms"] / args.steps},
             "gpu_launches": int(dev_run["launches"]),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "correspond_kernel (in-place incremental transform + exact 1-NN "
-                         "correspondence search over the LBVH)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "iterate_kernel<point-to-plane> (one launch per ICP iteration: in-place "
+                         "incremental transform + exact 1-NN over the LBVH + estimator reduction + last-block solve)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic_of("iterate_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
+                         "search_only_algorithmic_bytes": 40.0 * n,
                          "launches_timed": int(prof_run["iterate_launches"]),
                          "timed_in": "second pass of the same K steps with per-kernel CUDA events on the launch stream"},
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": host_threads(), "kind": "port",
-                             "sample": cpu_sample},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
+            "parity": parity,
             "breakdown_ms_per_step": {"build": prof_run["build_ms"] / args.steps,
-                                      "correspond": prof_run["iterate_ms"] / args.steps,
-                                      "reduce_solve": prof_run["solve_ms"] / args.steps,
+                                      "iterate": prof_run["iterate_ms"] / args.steps,
+                                      "unfused_reduce_solve": prof_run["solve_ms"] / args.steps,
                                       "whole_step_with_events": prof_run["total_ms"] / args.steps,
                                       "icp_iterations": prof_run["iters"]},
+            "results_gathered": {"ranks": int(np.isfinite(table[:, 0]).sum()),
+                                 "all_converged": bool(np.nansum(table[:, 16]) == world)},
+            "batch256": sub,
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish_dist(dist, world)
     return 0
 
 
-def run_batch(args, W, batch, torch, dist, rank, local_rank, world, dev):
-    """BASELINE.json configs[4]: 256 independent 200k-point ICP (SVD estimator, full resolution)
-    scan-to-map alignments; scan k -> rank k mod world; 8 host threads per rank (measured: 4 -> 2498, 8 -> 2855, 16 -> 2833 scans/s on
-    one GPU), each with its own
-    handle / stream (MultiMatcher's structure); one NCCL all-gather of the 256 result records."""
-    import threading
+def finish_dist(dist, world):
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
+
+# ================================================================================================
+# batch256 (BASELINE.json configs[4])
+# ================================================================================================
+def batch256(args, W, batch, torch, dist, rank, local_rank, world, dev, steps=None):
+    """256 independent 200k-point ICP (SVD estimator, full resolution) scan-to-map alignments through the C
+    batch API (wavecu_batch_*): scan k -> rank k mod world; on every rank `workers` concurrent matches, each
+    on its own handle / streams; the shared map broadcast from rank 0 (NCCL inside the library) and indexed
+    once per GPU; ONE all-gather of the 256 result records at the end of a step."""
     from libwave_b200 import synth
+    steps = steps or args.steps
     n_scans, n_pts, workers = 256, 200_000, int(os.environ.get("WAVE_BATCH_WORKERS", "8"))
     mine = batch.shard_scan_ids(n_scans, rank, world)
+    per = (n_scans + world - 1) // world
     sources, target = synth.scan_batch(n_pts, 0, ids=mine)
-    tgt = synth.to_xyzw(target)
-    srcs = {k: synth.to_xyzw(s) for k, s in zip(mine, sources)}
-    matchers = [W.ICPMatcher(W.ICPMatcherParams(res=-1), device=local_rank) for _ in range(workers)]
-    h_tgt = torch.from_numpy(tgt).pin_memory()
-    h_src = {k: torch.from_numpy(v).pin_memory() for k, v in srcs.items()}
+    h_src = [torch.from_numpy(synth.to_xyzw(s)).pin_memory() for s in sources]
+    scans = [t.numpy() for t in h_src]
+    sb = batch.ScanBatch(W.ICPMatcherParams(res=-1), devices=[local_rank], workers_per_device=workers)
+    if world > 1:
+        def exchange(raw):
+            box = [raw]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        sb.init_comm(rank, world, exchange)
+        sb.broadcast_map(synth.to_xyzw(target) if rank == 0 else None, n_pts, root=0)
+    else:
+        sb.set_map(synth.to_xyzw(target))
+
+    from libwave_b200 import capi
 
     def step():
-        local, pairs = {}, [0] * workers
+        recs = sb.match(scans, scan_ids=mine)
+        local = (capi.BatchRecordC * per)()
+        for i in range(per):
+            if i < len(mine):
+                local[i] = recs[i]
+            else:
+                local[i].scan_id = -1
+        allr = sb.allgather(local, per)
+        pairs = sum(r.iterations for r in recs[:len(mine)]) * n_pts
+        return allr, pairs
 
-        def work(w):
-            m = matchers[w]
-            for k in mine[w::workers]:
-                m.setRef(h_src[k].numpy())       # MultiMatcher::spin: setRef, setTarget, match
-                m.setTarget(h_tgt.numpy())
-                ok = m.match()
-                local[k] = batch.pack_record(m.getResult(), ok, m.iterations)
-                pairs[w] += m.iterations * n_pts
-        th = [threading.Thread(target=work, args=(w,)) for w in range(workers)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        table = batch.gather_records(local, n_scans, device=dev)
-        return table, sum(pairs)
-
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(2):
         step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     pairs = 0
-    for _ in range(args.steps):
-        table, p = step()
+    for _ in range(steps):
+        allr, p = step()
         pairs += p
     torch.cuda.synchronize()
     total_ms = (time.perf_counter() - t0) * 1e3
     total_ms, pairs_all = batch.reduce_timing(total_ms, float(pairs), device=dev)
+    table = batch.records_to_table(allr, n_scans)
+    conv = int(np.nansum(table[:, 16]))
+    err = float(np.nanmax(np.abs(table[:, [3, 7, 11]] - synth.T_TRUE[:3, 3])))
+    del sb
+    return {
+        "metric": METRIC.replace("1M-pt ICP", "256 x 200k-pt ICP batch"), "value": pairs_all / (total_ms * 1e-3),
+        "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": 2,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "256 independent 200k-point ICP scan-to-map alignments (SVD estimator, res=-1) through "
+                               f"wavecu_batch_*: scan k -> rank k mod N, {workers} concurrent matches per GPU, page-locked "
+                               "host scans (H2D inside), shared map indexed once per GPU, one all-gather of the records",
+                   "timing": "host wall clock around whole steps (matches overlap on several streams per GPU), max over "
+                             "ranks"},
+        "scans_per_s": n_scans * steps / (total_ms * 1e-3), "scans_matched": int(np.isfinite(table[:, 16]).sum()),
+        "scans_converged": conv, "max_translation_error_m": err,
+    }
+
+
+# ================================================================================================
+# gicp500k (BASELINE.json configs[2])
+# ================================================================================================
+GICP_N = 500_000
+GICP_METRIC = "point-pairs/s (500k-pt GICP; pair = source point x cost evaluation)"
+
+
+def gicp_config():
+    return {"workload": "GICPMatcher (k=10 covariances, BFGS), two noisy 500k-point synthetic Velodyne-style scans, "
+                        "res=-1, reference default parameters; covariances and both trees rebuilt every step",
+            "n_source": GICP_N, "n_target": GICP_N,
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def gicp_cpu_sample(src, tgt, threads):
+    from oracle import oracle as O
+    O.build()
+
+    def work(_):
+        r = O.gicp_align(src, tgt)
+        return r.evaluations * src.shape[0], r
+    out, dt = run_threads(work, threads)
+    sample = (f"{threads} concurrent single-threaded oracle GICP matches of the same 500k/500k pair, run to "
+              f"convergence ({out[0][1].iterations} outer iterations, {out[0][1].evaluations} evaluations each); "
+              f"{dt:.1f} s wall")
+    return sum(o[0] for o in out) / dt, sample, dt, out[0][1]
+
+
+def run_reference_gicp(args):
+    from libwave_b200 import synth
+    src, tgt = synth.scan_pair(GICP_N)
+    threads = host_threads()
+    v, sample, dt, _ = gicp_cpu_sample(src, tgt, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": GICP_METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+        "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": gicp_config(),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+    return 0
+
+
+def run_gicp(args, W, batch, torch, dist, rank, local_rank, world, dev):
+    from libwave_b200 import synth
+    src, tgt = synth.scan_pair(GICP_N, scan_id=None if rank == 0 else rank)
+    xs, xt = synth.to_xyzw(src), synth.to_xyzw(tgt)
+    n = xs.shape[0]
+    stream = torch.cuda.Stream(device=dev)
+    m = W.GICPMatcher(W.GICPMatcherParams(res=-1), device=local_rank, stream=stream.cuda_stream)
+    d_src, d_tgt = torch.from_numpy(xs).to(dev), torch.from_numpy(xt).to(dev)
+    h_src, h_tgt = torch.from_numpy(xs).pin_memory(), torch.from_numpy(xt).pin_memory()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        m.setRefDevice(d_src.data_ptr(), n)
+        m.setTargetDevice(d_tgt.data_ptr(), n)
+        return m.match()
+
+    def step_host():
+        m.setRef(h_src.numpy())
+        m.setTarget(h_tgt.numpy())
+        return m.match()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            flush.fill_(1)
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms, pairs, launches, cost_ms, cost_n = [], 0, 0, 0.0, 0
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            ok = fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+            st = m.stats()
+            pairs += st["evaluations"] * n
+            launches += st["kernel_launches"]
+            cost_ms += st["cost_kernel_ms"]
+            cost_n += st["cost_kernel_launches"]
+            assert ok
+        t, p = batch.reduce_timing(float(sum(ms)), float(pairs), device=dev)
+        return {"total_ms": t, "pairs_all": p, "launches": launches, "cost_ms": cost_ms, "cost_n": cost_n}
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
+    dev_run = timed(step_device, args.steps, args.warmup)
+    e2e_run = timed(step_host, args.steps, args.warmup)
+    m.set_profiling(True)
+    prof = timed(step_device, args.steps, 1)
+    m.set_profiling(False)
+    if sampler:
+        sampler.mark_end()
+    clocks = sampler.finish() if sampler else None
     if rank == 0:
-        conv = int(np.nansum(table[:, 16]))
-        err = float(np.nanmax(np.abs(table[:, [3, 7, 11]] - synth.T_TRUE[:3, 3])))
+        st = m.stats()
+        peak, peak_src = peak_hbm()
+        alg = 60.0 * st["n_corr"]     # 16 B source + 4 B index + 16 B target gather + 24 B Mahalanobis (sym. fp32-compact)
+        mean_ms = prof["cost_ms"] / max(1, prof["cost_n"])
+        achieved = alg / (mean_ms * 1e-3) / 1e9 if mean_ms > 0 else 0.0
+        dt_true, dr_true = pose_error(m.getResult(), synth.T_TRUE)
+        threads = host_threads()
+        parity, cpu_v, cpu_sample = None, None, "skipped (--skip-cpu)"
+        if not args.skip_cpu:
+            cpu_v, cpu_sample, _, ref = gicp_cpu_sample(src, tgt, threads)
+            parity = {"oracle": "oracle.gicp_align on the same clouds (restated PCL GICP + BFGS, exact cost sums)",
+                      "outer_iterations": int(m.iterations), "oracle_outer_iterations": int(ref.iterations),
+                      "evaluations": int(st["evaluations"]), "oracle_evaluations": int(ref.evaluations),
+                      "correspondences_equal": bool(st["n_corr"] == ref.n_corr),
+                      "transform_bit_equal": bool(np.array_equal(m.getResult().astype(np.float32), ref.T)),
+                      "max_abs_T_diff": float(np.abs(m.getResult() - ref.T.astype(np.float64)).max()),
+                      "vs_ground_truth": {"translation_error_m": dt_true, "rotation_error_rad": dr_true,
+                                          "note": "the restated PCL algorithm itself stops this far from the truth on "
+                                                  "this pair (k = 10 neighbourhoods of a 7813-step ring are line "
+                                                  "segments); 1.6 cm / 0.6 cm at 10k / 200k points"}}
         print(json.dumps({
-            "metric": METRIC.replace("1M-pt ICP", "256 x 200k-pt ICP batch"), "value": pairs_all / (total_ms * 1e-3),
-            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "256 independent 200k-point ICP scan-to-map alignments (SVD estimator, res=-1), "
-                                   f"scan k -> rank k mod N, {workers} host threads per rank, host clouds (H2D inside)",
-                       "timing": f"host wall clock around whole steps (matches overlap on {workers} streams per GPU)"},
-            "scans_converged": conv, "max_translation_error_m": err,
-            "scans_per_s": n_scans * args.steps / (total_ms * 1e-3)}))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            "metric": GICP_METRIC, "value": dev_run["pairs_all"] / (dev_run["total_ms"] * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_run["total_ms"] / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": gicp_config(),
+            "e2e": {"value": e2e_run["pairs_all"] / (e2e_run["total_ms"] * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(2 * 16 * n), "d2h_bytes_per_step": 128,
+                    "ms_per_step": e2e_run["total_ms"] / args.steps},
+            "gpu_launches": int(dev_run["launches"]), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "gicp_cost_kernel (f, gradient and rotation accumulator of one BFGS "
+                         "evaluation; the Mahalanobis matrices are kept in fp64: 72 B/pair read, 60 B/pair algorithmic)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic_of("gicp_cost_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "mean_launch_ms": mean_ms, "launches_timed": int(prof["cost_n"])},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
+            "parity": parity}))
+    return 0
+
+
+# ================================================================================================
+# ndt1m5m (BASELINE.json configs[3])
+# ================================================================================================
+NDT_METRIC = "point-pairs/s (NDT 1M-pt scan vs 5M-pt map; pair = source point x derivative pass)"
+
+
+def ndt_config():
+    return {"workload": "NDTMatcher, 0.5 m voxels, 1M-point synthetic scan vs the 5M-point map (union of 5 scans along a "
+                        "4 m baseline), step_size=3, max_iter=100, t_eps=1e-8, More-Thuente line search (PCL >= 1.9); "
+                        "voxel grid of the map rebuilt every step",
+            "n_source": N_POINTS, "res": 0.5, "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def ndt_clouds(rank):
+    from libwave_b200 import synth
+    rings, az = synth.SIZES[N_POINTS]
+    scan = synth.velodyne_scan(rings, az, None, synth.SOURCE_SEED if rank == 0 else 1000 + rank, n_points=N_POINTS)
+    big = synth.map_cloud(5, N_POINTS)
+    return scan, big
+
+
+def ndt_cpu_sample(scan, big, threads):
+    from oracle import oracle as O
+    O.build()
+
+    def work(_):
+        r = O.ndt_align(scan, big, res=0.5)
+        return (len(r.steps) + 1) * scan.shape[0], r
+    out, dt = run_threads(work, threads)
+    sample = (f"{threads} concurrent single-threaded oracle NDT matches of the same scan/map pair, run to convergence "
+              f"({out[0][1].iterations} iterations each); {dt:.1f} s wall; pairs counted as (iterations + 1) passes")
+    return sum(o[0] for o in out) / dt, sample, dt, out[0][1]
+
+
+def run_reference_ndt(args):
+    scan, big = ndt_clouds(0)
+    threads = min(host_threads(), 8)   # every match holds its own copy of the 5M-point grid
+    v, sample, dt, _ = ndt_cpu_sample(scan, big, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": NDT_METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": ndt_config(),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+    return 0
+
+
+def run_ndt(args, W, batch, torch, dist, rank, local_rank, world, dev):
+    from libwave_b200 import synth
+    scan, big = ndt_clouds(rank)
+    xs, xt = synth.to_xyzw(scan), synth.to_xyzw(big)
+    n, nt = xs.shape[0], xt.shape[0]
+    stream = torch.cuda.Stream(device=dev)
+    m = W.NDTMatcher(W.NDTMatcherParams(res=0.5), device=local_rank, stream=stream.cuda_stream)
+    d_src, d_tgt = torch.from_numpy(xs).to(dev), torch.from_numpy(xt).to(dev)
+    h_src, h_tgt = torch.from_numpy(xs).pin_memory(), torch.from_numpy(xt).pin_memory()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        m.setRefDevice(d_src.data_ptr(), n)
+        m.setTargetDevice(d_tgt.data_ptr(), nt)
+        return m.match()
+
+    def step_host():
+        m.setRef(h_src.numpy())
+        m.setTarget(h_tgt.numpy())
+        return m.match()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            flush.fill_(1)
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms, pairs, launches, der_ms, der_n = [], 0, 0, 0.0, 0
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            ok = fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+            st = m.stats()
+            pairs += st["derivative_passes"] * n
+            launches += st["kernel_launches"]
+            der_ms += st["derivative_kernel_ms"]
+            der_n += st["derivative_passes"]
+            assert ok
+        t, p = batch.reduce_timing(float(sum(ms)), float(pairs), device=dev)
+        return {"total_ms": t, "pairs_all": p, "launches": launches, "der_ms": der_ms, "der_n": der_n}
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
+    dev_run = timed(step_device, args.steps, args.warmup)
+    e2e_run = timed(step_host, args.steps, args.warmup)
+    m.set_profiling(True)
+    prof = timed(step_device, args.steps, 1)
+    m.set_profiling(False)
+    if sampler:
+        sampler.mark_end()
+    clocks = sampler.finish() if sampler else None
+    if rank == 0:
+        st = m.stats()
+        peak, peak_src = peak_hbm()
+        alg = 16.0 * n + 76.0 * st["n_cells"]     # fp64 voxel statistics are kept for parity: 76 B/voxel (SURVEY 8(d))
+        mean_ms = prof["der_ms"] / max(1, prof["der_n"])
+        achieved = alg / (mean_ms * 1e-3) / 1e9 if mean_ms > 0 else 0.0
+        dt_true, dr_true = pose_error(m.getResult(), synth.T_TRUE)
+        threads = min(host_threads(), 8)
+        parity, cpu_v, cpu_sample = None, None, "skipped (--skip-cpu)"
+        if not args.skip_cpu:
+            cpu_v, cpu_sample, _, ref = ndt_cpu_sample(scan, big, threads)
+            dt_o, dr_o = pose_error(m.getResult(), ref.T)
+            parity = {"oracle": "oracle.ndt_align on the same clouds (restated PCL NDT, More-Thuente line search)",
+                      "iterations": int(m.iterations), "oracle_iterations": int(ref.iterations),
+                      "iterations_equal": bool(m.iterations == ref.iterations),
+                      "vs_oracle": {"translation_m": dt_o, "rotation_rad": dr_o,
+                                    "within_1e-4m_1e-5rad": bool(dt_o < 1e-4 and dr_o < 1e-5)},
+                      "vs_ground_truth": {"translation_error_m": dt_true, "rotation_error_rad": dr_true}}
+        print(json.dumps({
+            "metric": NDT_METRIC, "value": dev_run["pairs_all"] / (dev_run["total_ms"] * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_run["total_ms"] / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(ndt_config(), n_target=int(nt), n_cells=int(st["n_cells"])),
+            "e2e": {"value": e2e_run["pairs_all"] / (e2e_run["total_ms"] * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(16 * (n + nt)), "d2h_bytes_per_step": 128,
+                    "ms_per_step": e2e_run["total_ms"] / args.steps},
+            "gpu_launches": int(dev_run["launches"]), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "ndt_derivative_kernel (score, gradient and Hessian over the 27-voxel "
+                         "neighbourhood of every transformed source point)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic_of("ndt_derivative_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "mean_launch_ms": mean_ms, "launches_timed": int(prof["der_n"])},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
+            "parity": parity, "accuracy": {"translation_error_m": dt_true, "rotation_error_rad": dr_true}}))
     return 0
 
 
@@ -413,10 +814,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--workload", default="icp1m", choices=["icp1m", "batch256"],
-                    help="icp1m: BASELINE.json configs[1] (default, the headline); batch256: configs[4], 256 "
-                         "independent 200k-point scan-to-map ICP alignments sharded over the ranks")
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline and parity legs (profiling runs)")
+    ap.add_argument("--no-batch", action="store_true", help="icp1m: omit the batch256 sub-record")
+    ap.add_argument("--workload", default="icp1m", choices=["icp1m", "batch256", "gicp500k", "ndt1m5m"],
+                    help="icp1m: BASELINE.json configs[1] (default, the headline, with a batch256 sub-record); "
+                         "batch256: configs[4] alone; gicp500k: configs[2]; ndt1m5m: configs[3]")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -106,6 +106,15 @@ int wavecu_icp_set_source_device(wavecu_icp *h, const void *d_xyzw, size_t n);
 int wavecu_icp_set_target_device(wavecu_icp *h, const void *d_xyzw, size_t n);
 int wavecu_icp_set_target_normals_device(wavecu_icp *h, const void *d_nxyzw, size_t n);
 
+/* Scan-to-map batches: many source scans against one target ("map").  The map is uploaded to one
+ * handle, its search structure built once (wavecu_icp_build_target), and any number of other handles on
+ * the same device then match against it read-only (wavecu_icp_share_target; owner = NULL detaches) -
+ * instead of every MultiMatcher worker uploading and indexing the same cloud for every job
+ * (impl/multi_matcher_impl.hpp:45-46 calls setTarget per job).  The owner must outlive its sharers and
+ * must not change its target while they are matching.  Full resolution (res <= 0) only. */
+int wavecu_icp_build_target(wavecu_icp *h);
+int wavecu_icp_share_target(wavecu_icp *h, wavecu_icp *owner);
+
 /* Which kernel runs the per-iteration exact 1-NN search (results are identical bit for bit):
  * WAVECU_SEARCH_TREE - one query per lane walking the LBVH (default); WAVECU_SEARCH_TILED - a CTA per
  * tile of Morton-consecutive queries, target runs staged into shared memory with cp.async.bulk, the
@@ -200,6 +209,10 @@ int wavecu_ndt_derivatives(wavecu_ndt *h, const double pose6[6], const float T16
                            double H36[36]);
 /* n_cells: the normal-distribution cells (>= 6 points, usable covariance) - what wavecu_ndt_grid lists */
 int wavecu_ndt_stats(wavecu_ndt *h, long long *kernel_launches, long long *derivative_passes, int *n_cells);
+/* with profiling on, every derivative pass of the following matches is bracketed by CUDA events on the
+ * handle's stream; wavecu_ndt_timing returns their summed device time (of the last match) */
+int wavecu_ndt_set_profiling(wavecu_ndt *h, int enabled);
+int wavecu_ndt_timing(wavecu_ndt *h, double *derivative_kernel_ms);
 
 /* ---- GICPMatcher (include/wave/matching/gicp.hpp:30-65, src/gicp.cpp:20-64) -------------------------
  * Field-for-field mirror of wave::GICPMatcherParams (gicp.hpp:34-38). */
@@ -231,12 +244,52 @@ int wavecu_gicp_covariances(wavecu_gicp *h, int which, double *covs9, size_t *n)
 int wavecu_gicp_cloud(wavecu_gicp *h, int which, float *xyzw, size_t *n);
 int wavecu_gicp_stats(wavecu_gicp *h, long long *kernel_launches, long long *evaluations,
                       long long *inner_iterations, size_t *n_corr);
+/* with profiling on, every cost / gradient evaluation kernel of the following matches is bracketed by CUDA
+ * events on the handle's stream; wavecu_gicp_timing returns their summed device time and count */
+int wavecu_gicp_set_profiling(wavecu_gicp *h, int enabled);
+int wavecu_gicp_timing(wavecu_gicp *h, double *cost_kernel_ms, long long *cost_kernel_launches);
 
 /* pcl::VoxelGrid<pcl::PointXYZ>::filter (src/icp.cpp:81-90,106-113; src/gicp.cpp:39-40,49-50):
  * one centroid per occupied voxel in ascending voxel index; out_xyzw needs room for n points.
  * *filtered = 0 when the grid would overflow int32 and the input is passed through unchanged. */
 int wavecu_voxel_grid(int device, const float *xyzw, size_t n, float leaf, float *out_xyzw, size_t *n_out,
                       int *filtered);
+
+/* ---- batches of independent alignments (wave::MultiMatcher, multi_matcher.hpp:30-96) -------------------
+ * One batch object spreads scans over the GPUs of this process (devices[]; n_devices = 0: every visible
+ * device), workers_per_device concurrent matches per GPU, each on its own handle and streams.  With a map
+ * (wavecu_batch_set_map, or wavecu_batch_broadcast_map when only one rank of a multi-process job holds it)
+ * every scan is matched against the same target, uploaded and indexed once per GPU.  Multi-process jobs
+ * (one process per GPU, BASELINE.json configs[4]) create a communicator from an id made on one rank and
+ * handed to the others by the caller's own means (a file, MPI, torch.distributed ...); the only
+ * collectives are the optional map broadcast and ONE all-gather of the result records at the end. */
+typedef struct {
+    double T[16];      /* Matcher::result, row major */
+    double info[36];   /* Matcher::information (estimateInfo: ends as estimateLUMold, src/icp.cpp:135-142) */
+    int converged;     /* match() return value */
+    int iterations;
+    int scan_id;       /* the caller's id of this scan (multi_matcher.hpp:57); -1: unused slot */
+    int device;        /* CUDA ordinal that matched it */
+} wavecu_batch_record;
+
+typedef struct wavecu_batch wavecu_batch;
+int wavecu_batch_create(const wavecu_icp_params *params, const int *devices, int n_devices, int workers_per_device,
+                        wavecu_batch **out);
+int wavecu_batch_destroy(wavecu_batch *b);
+int wavecu_batch_device_count(wavecu_batch *b);
+int wavecu_batch_set_map(wavecu_batch *b, const float *xyzw, size_t n);
+/* scans[i]: host cloud of n_points[i] points; scan_ids may be NULL (ids 0..n-1); targets NULL: match against
+ * the map, else targets[i] / n_targets[i] per scan (MultiMatcher::insert(id, src, target)); with_info != 0
+ * also fills the information matrix; out[i] receives the record of scans[i].  Blocks until all are done. */
+int wavecu_batch_match(wavecu_batch *b, const float *const *scans, const size_t *n_points, const int *scan_ids,
+                       int n_scans, const float *const *targets, const size_t *n_targets, int with_info,
+                       wavecu_batch_record *out);
+/* multi-process: 128-byte NCCL unique id (make it on one rank), communicator on the batch's first device */
+int wavecu_batch_unique_id(void *id128);
+int wavecu_batch_init_comm(wavecu_batch *b, const void *id128, int rank, int world);
+int wavecu_batch_broadcast_map(wavecu_batch *b, const float *xyzw_on_root, size_t n, int root);
+/* every rank passes n_local records (same count everywhere); all receives world * n_local, in rank order */
+int wavecu_batch_allgather(wavecu_batch *b, const wavecu_batch_record *local, int n_local, wavecu_batch_record *all);
 
 const char *wavecu_last_error(void);
 int wavecu_device_count(void);

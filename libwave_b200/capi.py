@@ -38,6 +38,12 @@ class GicpParamsC(C.Structure):
                 ("res", C.c_float)]
 
 
+class BatchRecordC(C.Structure):
+    """wavecu_batch_record: one scan's result (Matcher::result, Matcher::information, flags)."""
+    _fields_ = [("T", C.c_double * 16), ("info", C.c_double * 36), ("converged", C.c_int), ("iterations", C.c_int),
+                ("scan_id", C.c_int), ("device", C.c_int)]
+
+
 class StatsC(C.Structure):
     _fields_ = [("build_ms", C.c_double), ("iterate_ms", C.c_double), ("solve_ms", C.c_double),
                 ("total_ms", C.c_double), ("iterate_launches", C.c_longlong), ("kernel_launches", C.c_longlong),
@@ -74,6 +80,18 @@ SIGNATURES = {
     "wavecu_nn_search": (C.c_int, [_vp, _fp, _sz, C.c_double, _ip, _fp]),
     "wavecu_nn_search_device": (C.c_int, [_vp, _vp, _sz, C.c_double, _vp, _vp, C.c_int, _fp]),
     "wavecu_icp_set_search": (C.c_int, [_vp, C.c_int]),
+    "wavecu_icp_build_target": (C.c_int, [_vp]),
+    "wavecu_icp_share_target": (C.c_int, [_vp, _vp]),
+    "wavecu_batch_create": (C.c_int, [C.POINTER(IcpParamsC), _ip, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "wavecu_batch_destroy": (C.c_int, [_vp]),
+    "wavecu_batch_device_count": (C.c_int, [_vp]),
+    "wavecu_batch_set_map": (C.c_int, [_vp, _fp, _sz]),
+    "wavecu_batch_match": (C.c_int, [_vp, C.POINTER(_fp), _szp, _ip, C.c_int, C.POINTER(_fp), _szp, C.c_int,
+                                     C.POINTER(BatchRecordC)]),
+    "wavecu_batch_unique_id": (C.c_int, [_vp]),
+    "wavecu_batch_init_comm": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "wavecu_batch_broadcast_map": (C.c_int, [_vp, _fp, _sz, C.c_int]),
+    "wavecu_batch_allgather": (C.c_int, [_vp, C.POINTER(BatchRecordC), C.c_int, C.POINTER(BatchRecordC)]),
     "wavecu_ndt_default_params": (None, [C.POINTER(NdtParamsC)]),
     "wavecu_ndt_create": (C.c_int, [C.POINTER(NdtParamsC), C.c_int, _vp, C.POINTER(_vp)]),
     "wavecu_ndt_destroy": (C.c_int, [_vp]),
@@ -86,6 +104,10 @@ SIGNATURES = {
     "wavecu_ndt_grid": (C.c_int, [_vp, _ip, _ip, _ip, _fp, _dp, _dp, C.c_int]),
     "wavecu_ndt_derivatives": (C.c_int, [_vp, _dp, _fp, _dp, _dp, _dp]),
     "wavecu_ndt_stats": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _ip]),
+    "wavecu_ndt_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "wavecu_ndt_timing": (C.c_int, [_vp, _dp]),
+    "wavecu_gicp_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "wavecu_gicp_timing": (C.c_int, [_vp, _dp, C.POINTER(C.c_longlong)]),
     "wavecu_gicp_default_params": (None, [C.POINTER(GicpParamsC)]),
     "wavecu_gicp_create": (C.c_int, [C.POINTER(GicpParamsC), C.c_int, _vp, C.POINTER(_vp)]),
     "wavecu_gicp_destroy": (C.c_int, [_vp]),

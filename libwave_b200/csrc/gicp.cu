@@ -328,6 +328,11 @@ struct GicpHandle {
     int n_blocks = 148 * 4;
     long long launches = 0, evaluations = 0, inner_iterations = 0;
     size_t n_corr = 0;
+    // optional per-kernel timing (CUDA events on the handle's stream around every cost-kernel launch)
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double cost_ms = 0;
+    long long cost_launches = 0;
 
     // ---- functor state (the pairs of the current outer iteration) ----
     long long m_pairs = 0;
@@ -441,9 +446,17 @@ struct GicpHandle {
         pose.scale = std::ldexp(1.0, sum_k);
         ++evaluations;
         const int seq = ++cost_seq;
+        if (profiling) {
+            if (!ev0) {
+                WCU_CHECK(cudaEventCreate(&ev0));
+                WCU_CHECK(cudaEventCreate(&ev1));
+            }
+            WCU_CHECK(cudaEventRecord(ev0, stream));
+        }
         gicp_cost_kernel<<<n_blocks, kGicpThreads, 0, stream>>>(src.cloud.d_sorted, (int) src.cloud.n, tgt.cloud.d_sorted,
                                                                 d_pos, d_mahal, pose, d_partial, d_ticket, h_sums,
                                                                 h_seq, seq);
+        if (profiling) WCU_CHECK(cudaEventRecord(ev1, stream));
         ++launches;
         WCU_CHECK(cudaGetLastError());
         // wait for the kernel's own hand-over instead of synchronising the stream
@@ -461,6 +474,13 @@ struct GicpHandle {
 #if defined(__x86_64__)
             __builtin_ia32_pause();
 #endif
+        }
+        if (profiling) {
+            float ms = 0;
+            WCU_CHECK(cudaEventSynchronize(ev1));
+            WCU_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+            cost_ms += ms;
+            ++cost_launches;
         }
         const double m = (double) m_pairs;
         if (f) *f = h_sums[0] / m;
@@ -486,6 +506,8 @@ struct GicpHandle {
         if (h_sums) cudaFreeHost(h_sums);
         if (h_seq) cudaFreeHost(h_seq);
         if (d_ticket) cudaFree(d_ticket);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -755,6 +777,8 @@ int GicpHandle::match(double *T_out, int *converged_out, int *iterations_out) {
     WCU_CHECK(cudaSetDevice(device));
     launches = evaluations = inner_iterations = 0;
     n_corr = 0;
+    cost_ms = 0;
+    cost_launches = 0;
     float transformation[16], previous[16];
     identity4(transformation);
     identity4(previous);
@@ -984,6 +1008,19 @@ int wavecu_gicp_stats(wavecu_gicp *w, long long *kernel_launches, long long *eva
     if (evaluations) *evaluations = w->h.evaluations;
     if (inner_iterations) *inner_iterations = w->h.inner_iterations;
     if (n_corr) *n_corr = w->h.n_corr;
+    return WAVECU_OK;
+}
+
+int wavecu_gicp_set_profiling(wavecu_gicp *w, int enabled) {
+    if (!w) return WAVECU_ERR_ARG;
+    w->h.profiling = enabled != 0;
+    return WAVECU_OK;
+}
+
+int wavecu_gicp_timing(wavecu_gicp *w, double *cost_kernel_ms, long long *cost_kernel_launches) {
+    if (!w) return WAVECU_ERR_ARG;
+    if (cost_kernel_ms) *cost_kernel_ms = w->h.cost_ms;
+    if (cost_kernel_launches) *cost_kernel_launches = w->h.cost_launches;
     return WAVECU_OK;
 }
 

@@ -160,6 +160,12 @@ struct IcpHandle {
     TraceRow *d_trace = nullptr;
     int trace_cap = 0;
     // tiled correspondence kernel (tile_nn.cuh): queries it hands to the LBVH walk
+    // scan-to-map batches: the target index of another handle on the same device, read-only here
+    // (wavecu_icp_share_target); its owner records ev_tgt_ready behind the build
+    IcpHandle *tgt_owner = nullptr;
+    cudaEvent_t ev_tgt_ready = nullptr;
+    unsigned long long tgt_epoch = 0, tgt_epoch_seen = 0;
+    TargetIndex &target() { return tgt_owner ? tgt_owner->tgt : tgt; }
     bool use_tile = false;
     bool use_fused = true;    // one launch per iteration (iterate_kernel); WAVECU_FUSED=0: correspond / reduce / solve
     unsigned *d_ticket = nullptr;
@@ -401,7 +407,18 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         if (rc) return rc;
     }
     have_result = false;
-    const size_t n_src = src.n, n_tgt = tgt.cloud.n;
+    TargetIndex &TG = target();
+    if (tgt_owner) {
+        if (TG.dirty) {
+            set_last_error("the shared target has not been built (wavecu_icp_build_target on its owner)");
+            return WAVECU_ERR_STATE;
+        }
+        if (tgt_epoch_seen != tgt_owner->tgt_epoch) {   // once per (re)build of the map
+            WCU_CHECK(cudaStreamWaitEvent(stream, tgt_owner->ev_tgt_ready, 0));
+            tgt_epoch_seen = tgt_owner->tgt_epoch;
+        }
+    }
+    const size_t n_src = src.n, n_tgt = TG.cloud.n;
     const int max_iter = std::max(prm.max_iter, 1);
     stats = wavecu_stats{};
     const long long launches0 = first_marked ? launches_mark : src.launches + tgt.cloud.launches;
@@ -437,20 +454,26 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         if (rc) return rc;
         WCU_CHECK(cudaEventRecord(ev_src_sorted, aux));
     }
-    if (tgt.dirty) {
-        rc = tgt.build();
+    if (!tgt_owner && TG.dirty) {
+        rc = TG.build();
         if (rc) return rc;
     }
     if (prm.estimator == WAVECU_EST_POINT_TO_PLANE) {
-        if (tgt.nrm_n == n_tgt) {
+        if (TG.nrm_n == n_tgt) {
             // the caller's normals are only read by the first reduction: their gather into Morton order is
             // queued behind the first correspondence launch, so that search does not wait for their upload
-            late_normals = tgt.nrm_dirty;
-            rc = tgt.reserve_sorted_normals();
+            // ... which only pays while that upload is still crossing PCIe; device-resident normals are
+            // gathered right away, and every iteration then runs as one fused launch
+            late_normals = !tgt_owner && TG.nrm_dirty && TG.nrm_up_pending;
+            rc = TG.reserve_sorted_normals();
             if (rc) return rc;
-        } else if (!tgt.normals_estimated) {
+            if (!tgt_owner && TG.nrm_dirty && !late_normals) {
+                rc = TG.sort_normals();
+                if (rc) return rc;
+            }
+        } else if (!TG.normals_estimated) {
             // no normals from the caller: estimate them on the target's own tree (k = 10 neighbours)
-            rc = tgt.estimate_normals(10);
+            rc = TG.estimate_normals(10);
             if (rc) return rc;
         }
     }
@@ -462,7 +485,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         fill_int_kernel<<<(unsigned) ((n_src + 255) / 256), 256, 0, stream>>>(d_nn_pos, -1, n_src);
         ++extra_launches;
     }
-    SetupArgs sa{src.d_bbox, tgt.cloud.d_bbox, d_mc, d_st, d_acc, prm.max_corr, d_fb_count, d_ticket};
+    SetupArgs sa{src.d_bbox, TG.cloud.d_bbox, d_mc, d_st, d_acc, prm.max_corr, d_fb_count, d_ticket};
     setup_kernel<<<1, 256, 0, stream>>>(sa);
     ++extra_launches;
     WCU_CHECK(cudaGetLastError());
@@ -472,9 +495,9 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     IterArgs ia;
     ia.cur = src.d_sorted;
     ia.n_src = (int) n_src;
-    ia.ix = tgt.index();
-    ia.tgt = tgt.cloud.d_sorted;
-    ia.nrm = tgt.d_nrm_sorted;
+    ia.ix = TG.index();
+    ia.tgt = TG.cloud.d_sorted;
+    ia.nrm = TG.d_nrm_sorted;
     ia.nn_pos = d_nn_pos;
     ia.nn_idx = d_nn_idx;
     ia.nn_d2 = d_nn_d2;
@@ -486,7 +509,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     *(volatile int *) h_progress = 0;
     SolveArgs so{d_st, d_mc, d_acc, d_trace, max_iter, prm.t_eps, prm.fit_eps, d_progress, 0, d_fb_count};
     const unsigned grid_nn = (unsigned) std::max<size_t>(1, (n_src + kIterThreads - 1) / kIterThreads);
-    const bool tiled = use_tile && tgt.want_boxes;
+    const bool tiled = use_tile && TG.want_boxes;
     const unsigned grid_tile = (unsigned) std::max<size_t>(1, (n_src + kTileQ - 1) / kTileQ);
     const unsigned grid_fb = std::min<unsigned>(grid_nn, 148u * 8u);
     const TileFallback fb{d_fb_count, d_fb_list};
@@ -512,7 +535,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
                 iterate_kernel<WAVECU_EST_SVD><<<grid_nn, kIterThreads, 0, stream>>>(fa);
             launches_total += 1;
         } else if (tiled) {
-            correspond_tile_kernel<<<grid_tile, kTileQ, sizeof(TileSmem), stream>>>(ia, tgt.boxes, fb);
+            correspond_tile_kernel<<<grid_tile, kTileQ, sizeof(TileSmem), stream>>>(ia, TG.boxes, fb);
             tile_fallback_kernel<<<grid_fb, kIterThreads, 0, stream>>>(ia, fb);
             launches_total += 4;
         } else {
@@ -525,7 +548,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         }
         if (late_normals) {
             late_normals = false;
-            rc = tgt.sort_normals();
+            rc = TG.sort_normals();
             if (rc) return rc;
         }
         if (!fused) {
@@ -717,6 +740,10 @@ int IcpHandle::match(double *T_out, int *converged, int *iterations) {
         set_last_error("the point-to-plane estimator needs per-point target normals: use res <= 0");
         return WAVECU_ERR_STATE;
     }
+    if (tgt_owner) {
+        set_last_error("a shared target is matched at full resolution only: use res <= 0");
+        return WAVECU_ERR_STATE;
+    }
     int rc = stash_originals();
     if (rc) return rc;
     const double user_max_corr = prm.max_corr;
@@ -848,7 +875,7 @@ int IcpHandle::info(int method, double *info_out) {
         oa.cur = src.d_sorted;
         oa.raw = src.d_raw;
         oa.n_src = (int) ns;
-        oa.ix = tgt.index();
+        oa.ix = target().index();
         oa.warm = d_nn_pos;
         oa.st = d_st;
         const double max2 = prm.max_corr * prm.max_corr;
@@ -863,7 +890,7 @@ int IcpHandle::info(int method, double *info_out) {
     la.cur = src.d_sorted;
     la.raw = src.d_raw;
     la.n_src = (int) ns;
-    la.tgt = tgt.cloud.d_sorted;
+    la.tgt = target().cloud.d_sorted;
     la.pos = pos;
     la.st = d_st;
     la.acc = d_acc;
@@ -1047,7 +1074,7 @@ int IcpHandle::info_censi(double *info_out) {
     ca.cur = src.d_sorted;
     ca.raw = src.d_raw;
     ca.n_src = (int) ns;
-    ca.tgt = tgt.cloud.d_sorted;
+    ca.tgt = target().cloud.d_sorted;
     ca.pos = d_nn_pos;
     ca.partial = d_censi;
     censi_kernel<<<blocks, kCensiThreads, 0, stream>>>(ca);
@@ -1103,7 +1130,7 @@ void IcpHandle::release() {
     if (h_st) cudaFreeHost(h_st);
     if (h_trace) cudaFreeHost(h_trace);
     for (auto e : ev_pool) cudaEventDestroy(e);
-    for (cudaEvent_t e : {ev_main, ev_src_sorted, ev_first})
+    for (cudaEvent_t e : {ev_main, ev_src_sorted, ev_first, ev_tgt_ready})
         if (e) cudaEventDestroy(e);
     if (aux) cudaStreamDestroy(aux);
     if (copy) cudaStreamDestroy(copy);
@@ -1272,6 +1299,43 @@ int wavecu_icp_trace(wavecu_icp *w, double *mse, int *n_corr, float *T_inc, int 
 int wavecu_icp_info(wavecu_icp *w, int method, double info_out[36]) {
     if (!w || !info_out) return WAVECU_ERR_ARG;
     return w->h.info(method, info_out);
+}
+
+int wavecu_icp_build_target(wavecu_icp *w) {
+    if (!w) return WAVECU_ERR_ARG;
+    IcpHandle &h = w->h;
+    WCU_CHECK(cudaSetDevice(h.device));
+    if (h.tgt_owner) {
+        set_last_error("this handle shares another handle's target");
+        return WAVECU_ERR_STATE;
+    }
+    if (h.tgt.dirty) {
+        const int rc = h.tgt.build();
+        if (rc) return rc;
+    }
+    if (!h.ev_tgt_ready) WCU_CHECK(cudaEventCreateWithFlags(&h.ev_tgt_ready, cudaEventDisableTiming));
+    WCU_CHECK(cudaEventRecord(h.ev_tgt_ready, h.stream));
+    ++h.tgt_epoch;
+    return WAVECU_OK;
+}
+
+int wavecu_icp_share_target(wavecu_icp *w, wavecu_icp *owner) {
+    if (!w) return WAVECU_ERR_ARG;
+    IcpHandle &h = w->h;
+    if (!owner) {
+        h.tgt_owner = nullptr;
+        h.have_result = false;
+        return WAVECU_OK;
+    }
+    if (owner == w || owner->h.device != h.device || owner->h.tgt_owner || !owner->h.ev_tgt_ready) {
+        set_last_error("share_target: the owner must be another handle on the same device whose target was built with "
+                       "wavecu_icp_build_target");
+        return WAVECU_ERR_ARG;
+    }
+    h.tgt_owner = &owner->h;
+    h.tgt_epoch_seen = 0;
+    h.have_result = false;
+    return WAVECU_OK;
 }
 
 int wavecu_icp_set_search(wavecu_icp *w, int mode) {

@@ -558,6 +558,11 @@ struct NdtHandle {
     long long launches = 0;
     long long derivative_passes = 0;
     float final_T[16];
+    // optional per-kernel timing (CUDA events on the handle's stream around every derivative pass)
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double derivative_ms = 0;
+    int last_iterations = 0;
 
     int init() {
         WCU_CHECK(cudaSetDevice(device));
@@ -651,9 +656,17 @@ struct NdtHandle {
         c.with_hessian = with_hessian ? 1 : 0;
         c.grid = grid;
         const int seq = ++pass_seq;
+        if (profiling) {
+            if (!ev0) {
+                WCU_CHECK(cudaEventCreate(&ev0));
+                WCU_CHECK(cudaEventCreate(&ev1));
+            }
+            WCU_CHECK(cudaEventRecord(ev0, stream));
+        }
         ndt_derivative_kernel<<<n_blocks, kNdtThreads, 0, stream>>>(d_src, (int) n_src, d_leaves, d_table_key,
                                                                      d_table_slot, table_mask, c, d_partial, d_ticket,
                                                                      h_sums, h_seq, seq);
+        if (profiling) WCU_CHECK(cudaEventRecord(ev1, stream));
         ++launches;
         ++derivative_passes;
         WCU_CHECK(cudaGetLastError());
@@ -671,6 +684,12 @@ struct NdtHandle {
 #if defined(__x86_64__)
             __builtin_ia32_pause();
 #endif
+        }
+        if (profiling) {
+            float ms = 0;
+            WCU_CHECK(cudaEventSynchronize(ev1));
+            WCU_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+            derivative_ms += ms;
         }
         *score = h_sums[0];
         for (int i = 0; i < 6; ++i) g[i] = h_sums[1 + i];
@@ -690,6 +709,7 @@ struct NdtHandle {
         for (int i = 0; i < 16; ++i) final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
         launches = 0;
         derivative_passes = 0;
+        derivative_ms = 0;
         bool converged = false;
         int nr_iterations = 0;
         if (grid_dirty || clamped_res() != resolution) {
@@ -811,6 +831,8 @@ struct NdtHandle {
         if (h_seq) cudaFreeHost(h_seq);
         if (d_ticket) cudaFree(d_ticket);
         if (d_n_valid) cudaFree(d_n_valid);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -963,6 +985,18 @@ int wavecu_ndt_stats(wavecu_ndt *w, long long *kernel_launches, long long *deriv
         }
         *n_cells = h.n_cells;
     }
+    return WAVECU_OK;
+}
+
+int wavecu_ndt_set_profiling(wavecu_ndt *w, int enabled) {
+    if (!w) return WAVECU_ERR_ARG;
+    w->h.profiling = enabled != 0;
+    return WAVECU_OK;
+}
+
+int wavecu_ndt_timing(wavecu_ndt *w, double *derivative_kernel_ms) {
+    if (!w) return WAVECU_ERR_ARG;
+    if (derivative_kernel_ms) *derivative_kernel_ms = w->h.derivative_ms;
     return WAVECU_OK;
 }
 

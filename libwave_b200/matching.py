@@ -296,11 +296,17 @@ class GICPMatcher(Matcher):
         capi.check(self._L.wavecu_gicp_cloud(self._h, which, _f(cloud), C.byref(n)))
         return cloud, covs.reshape(-1, 3, 3)
 
+    def set_profiling(self, on: bool):
+        capi.check(self._L.wavecu_gicp_set_profiling(self._h, int(on)))
+
     def stats(self) -> dict:
         a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
         n = C.c_size_t()
         capi.check(self._L.wavecu_gicp_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
-        return {"kernel_launches": a.value, "evaluations": b.value, "inner_iterations": c.value, "n_corr": n.value}
+        ms, k = C.c_double(), C.c_longlong()
+        capi.check(self._L.wavecu_gicp_timing(self._h, C.byref(ms), C.byref(k)))
+        return {"kernel_launches": a.value, "evaluations": b.value, "inner_iterations": c.value, "n_corr": n.value,
+                "cost_kernel_ms": ms.value, "cost_kernel_launches": k.value}
 
 
 @dataclasses.dataclass
@@ -393,10 +399,16 @@ class NDTMatcher(Matcher):
         capi.check(self._L.wavecu_ndt_derivatives(self._h, _d(pose), _f(T), C.byref(score), _d(g), _d(H)))
         return score.value, g, H.reshape(6, 6)
 
+    def set_profiling(self, on: bool):
+        capi.check(self._L.wavecu_ndt_set_profiling(self._h, int(on)))
+
     def stats(self) -> dict:
         a, b, c = C.c_longlong(), C.c_longlong(), C.c_int()
         capi.check(self._L.wavecu_ndt_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"kernel_launches": a.value, "derivative_passes": b.value, "n_cells": c.value}
+        ms = C.c_double()
+        capi.check(self._L.wavecu_ndt_timing(self._h, C.byref(ms)))
+        return {"kernel_launches": a.value, "derivative_passes": b.value, "n_cells": c.value,
+                "derivative_kernel_ms": ms.value}
 
 
 def voxel_grid(cloud, leaf: float, device: int = 0):
