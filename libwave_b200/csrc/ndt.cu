@@ -537,6 +537,11 @@ struct NdtHandle {
     bool own_stream = false;
     float4 *d_src = nullptr, *d_tgt = nullptr;
     size_t n_src = 0, n_tgt = 0, src_cap = 0, tgt_cap = 0;
+    // The derivative pass reads the source in Morton order: the 32 lanes of a warp then fall into the same
+    // few voxels (their cell records become broadcast loads, their hit counts agree) instead of 32
+    // different ones, as in a lidar driver's ring-major point order.  Sorted once per source cloud.
+    MortonCloud src_sorted;
+    bool src_dirty = true;
     bool grid_dirty = true;
     VoxelWork vox;
     NdtLeafDev *d_leaves = nullptr;
@@ -572,6 +577,9 @@ struct NdtHandle {
         }
         vox.device = device;
         vox.stream = stream;
+        src_sorted.device = device;
+        src_sorted.stream = stream;
+        src_sorted.key_bits = 10;   // 30 sorted bits: four radix passes; finer keys buy no more coherence
         n_blocks = 148 * 4;
         WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(double) * kNdtVals * (size_t) n_blocks));
         WCU_CHECK(cudaHostAlloc((void **) &h_sums, sizeof(double) * kNdtVals, cudaHostAllocMapped));
@@ -644,6 +652,18 @@ struct NdtHandle {
         return WAVECU_OK;
     }
 
+    int sort_source() {
+        if (!src_dirty) return WAVECU_OK;
+        src_dirty = false;
+        if (n_src == 0) return WAVECU_OK;
+        int rc = src_sorted.upload((const float *) d_src, n_src, true);
+        if (rc) return rc;
+        rc = src_sorted.sort(n_src);
+        launches += src_sorted.launches;
+        src_sorted.launches = 0;
+        return rc;
+    }
+
     // computeDerivatives at pose p (the source is transformed by the fp32 matrix of p)
     int derivatives(const double p[6], const float T[16], double gd1, double gd2, bool with_hessian, double *score,
                     double g[6], double H[36]) {
@@ -663,7 +683,7 @@ struct NdtHandle {
             }
             WCU_CHECK(cudaEventRecord(ev0, stream));
         }
-        ndt_derivative_kernel<<<n_blocks, kNdtThreads, 0, stream>>>(d_src, (int) n_src, d_leaves, d_table_key,
+        ndt_derivative_kernel<<<n_blocks, kNdtThreads, 0, stream>>>(src_sorted.d_sorted, (int) n_src, d_leaves, d_table_key,
                                                                      d_table_slot, table_mask, c, d_partial, d_ticket,
                                                                      h_sums, h_seq, seq);
         if (profiling) WCU_CHECK(cudaEventRecord(ev1, stream));
@@ -717,6 +737,10 @@ struct NdtHandle {
             if (rc) return rc;
         }
         if (n_src && n_tgt && grid_ok) {
+            {
+                const int rc = sort_source();
+                if (rc) return rc;
+            }
             const double outlier_ratio = 0.55;
             const double c1 = 10 * (1 - outlier_ratio);
             const double c2 = outlier_ratio / std::pow((double) resolution, 3);
@@ -824,6 +848,7 @@ struct NdtHandle {
     void release() {
         cudaSetDevice(device);
         vox.release();
+        src_sorted.release();
         for (void *p : {(void *) d_src, (void *) d_tgt, (void *) d_leaves, (void *) d_table_key, (void *) d_table_slot,
                         (void *) d_partial})
             if (p) cudaFree(p);
@@ -894,10 +919,12 @@ int wavecu_ndt_set_params(wavecu_ndt *w, const wavecu_ndt_params *params) {
 
 int wavecu_ndt_set_source(wavecu_ndt *w, const float *xyzw, size_t n) {
     if (!w || (!xyzw && n)) return WAVECU_ERR_ARG;
+    w->h.src_dirty = true;
     return w->h.upload(w->h.d_src, w->h.src_cap, w->h.n_src, xyzw, n, false);
 }
 int wavecu_ndt_set_source_device(wavecu_ndt *w, const void *d, size_t n) {
     if (!w || (!d && n)) return WAVECU_ERR_ARG;
+    w->h.src_dirty = true;
     return w->h.upload(w->h.d_src, w->h.src_cap, w->h.n_src, (const float *) d, n, true);
 }
 int wavecu_ndt_set_target(wavecu_ndt *w, const float *xyzw, size_t n) {
@@ -966,6 +993,10 @@ int wavecu_ndt_derivatives(wavecu_ndt *w, const double pose6[6], const float T16
     for (int i = 0; i < 6; ++i) g6[i] = 0;
     for (int i = 0; i < 36; ++i) H36[i] = 0;
     if (!h.grid_ok || !h.n_src) return WAVECU_OK;
+    {
+        const int rc = h.sort_source();
+        if (rc) return rc;
+    }
     const double o = 0.55, c1 = 10 * (1 - o), c2 = o / std::pow((double) h.resolution, 3), d3 = -std::log(c2);
     const double gd1 = -std::log(c1 + c2) - d3;
     const double gd2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / gd1);
