@@ -48,6 +48,15 @@ class ICPMatcher : public Matcher<PCLPointCloudPtr> {
     /// unit normals of the target, one xyz(w) record per target point (point-to-plane only)
     void setTargetNormals(const PCLPointCloudPtr &normals);
 
+    /// Extension for scan-to-map batches (not in the reference): finish this matcher's target now
+    /// (upload + search structure) so that other matchers on the same GPU can match against it ...
+    void buildTarget();
+    /// ... and make this matcher use `owner`'s target, read-only, instead of one of its own
+    /// (nullptr detaches).  The owner must outlive its sharers; full resolution (res <= 0) only.
+    void shareTarget(ICPMatcher *owner);
+    /// CUDA ordinal this matcher runs on (WAVE_MATCHING_DEVICE)
+    int device() const { return device_; }
+
     /// blocks until finished; false if ICP did not converge
     bool match();
     /// information matrix of the last match (see src/host/icp.cpp for the fall-through semantics)
@@ -58,6 +67,7 @@ class ICPMatcher : public Matcher<PCLPointCloudPtr> {
  private:
     wavecu_icp *handle = nullptr;
     PCLPointCloudPtr ref, target;
+    int device_ = 0;
 };
 
 }  // namespace wave

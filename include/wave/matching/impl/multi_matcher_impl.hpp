@@ -5,6 +5,28 @@
 
 namespace wave {
 
+namespace detail {
+// matchers that can read another matcher's target (ICPMatcher::shareTarget)
+template <class T, class = void>
+struct can_share_target : std::false_type {};
+template <class T>
+struct can_share_target<T, decltype(void(std::declval<T &>().shareTarget(static_cast<T *>(nullptr))))> : std::true_type {};
+
+template <class T>
+void attach_map(T &matcher, const std::vector<T *> &owners) {
+    if constexpr (can_share_target<T>::value) {
+        for (T *o : owners)
+            if (o->device() == matcher.device()) {
+                matcher.shareTarget(o);
+                return;
+            }
+    } else {
+        (void) matcher;
+        (void) owners;
+    }
+}
+}  // namespace detail
+
 template <class T, class R>
 MultiMatcher<T, R>::~MultiMatcher() {
     {
@@ -15,6 +37,32 @@ MultiMatcher<T, R>::~MultiMatcher() {
     this->op_condition.notify_all();
     for (auto &worker : this->pool) worker.join();
     for (T *m : this->matchers) delete m;
+    for (T *m : this->map_owners) delete m;
+}
+
+template <class T, class R>
+void MultiMatcher<T, R>::setMap(const PCLPointCloudPtr &map) {
+    // one owner per device the workers sit on; each worker then reads its device's owner
+    for (T *m : this->map_owners) delete m;
+    this->map_owners.clear();
+    for (T *worker : this->matchers) {
+        T *owner = nullptr;
+        for (T *o : this->map_owners)
+            if (o->device() == worker->device()) owner = o;
+        if (!owner) {
+            // a new matcher lands on the next device of the round-robin; keep asking until it is the right one
+            for (int tries = 0; tries < 64 && !owner; ++tries) {
+                T *cand = new T(R(this->config));
+                if (cand->device() == worker->device()) owner = cand;
+                else delete cand;
+            }
+            if (!owner) throw std::runtime_error("MultiMatcher::setMap: no matcher could be placed on the worker's device");
+            owner->setTarget(map);
+            owner->buildTarget();
+            this->map_owners.push_back(owner);
+        }
+        worker->shareTarget(owner);
+    }
 }
 
 template <class T, class R>
@@ -46,7 +94,8 @@ void MultiMatcher<T, R>::spin(int threadid) {
         // and remaining_matches still decrements
         try {
             matcher.setRef(std::get<1>(job));
-            matcher.setTarget(std::get<2>(job));
+            if (std::get<2>(job)) matcher.setTarget(std::get<2>(job));
+            else detail::attach_map(matcher, this->map_owners);   // null target: the shared map (setMap)
             matcher.match();
             matcher.estimateInfo();
         } catch (const std::exception &e) {

@@ -16,8 +16,11 @@
 #include <exception>
 #include <mutex>
 #include <queue>
+#include <stdexcept>
 #include <thread>
 #include <tuple>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "wave/matching/matcher.hpp"
@@ -42,6 +45,10 @@ class MultiMatcher {
     bool done();
     /// pops the oldest finished result; blocks while results are pending; false once drained
     bool getResult(int *id, Eigen::Affine3d *transform, Mat6 *info);
+    /// Extension for scan-to-map batches (not in the reference; matchers with shareTarget(), i.e.
+    /// ICPMatcher): every job inserted with a null target is matched against `map`, which is uploaded
+    /// and indexed once per GPU instead of once per job.  Call while no job is pending.
+    void setMap(const PCLPointCloudPtr &map);
 
  private:
     const int n_thread;
@@ -52,6 +59,7 @@ class MultiMatcher {
     std::queue<std::tuple<int, Eigen::Affine3d, Mat6>> output;
     std::vector<std::thread> pool;
     std::vector<T *> matchers;
+    std::vector<T *> map_owners;   // one per device in use (setMap)
 
     std::mutex ip_mutex, op_mutex, cnt_mutex;
     std::condition_variable ip_condition, op_condition;

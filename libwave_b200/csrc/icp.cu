@@ -358,6 +358,7 @@ int IcpHandle::set_target(const float *xyzw, size_t n, bool from_device) {
     WCU_CHECK(cudaSetDevice(device));
     int rc = on_set_target(from_device);
     if (rc) return rc;
+    tgt_owner = nullptr;   // a target of its own ends the sharing of another handle's
     rc = tgt.set_points(xyzw, n, from_device);
     if (rc) return rc;
     if (!(prm.res > 0) && n) {  // full resolution: build the search tree behind the copy

@@ -408,6 +408,7 @@ int run_captured(GraphCache &cache, cudaStream_t stream, const unsigned long lon
                  F &&enqueue) {
     if (!graphs_enabled()) return enqueue();
     if (!cache.matches(key)) {
+        if (!cache.seen_before(key)) return enqueue();   // first sight of this key: plain launches
         cache.release();
         const long long before = counter;
         WCU_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));

@@ -25,6 +25,20 @@ struct GraphCache {
     cudaGraphExec_t exec = nullptr;
     unsigned long long key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long launches = 0;
+    // A sequence is captured only when the same key comes twice in a row: clouds whose size changes on
+    // every call (real scans, voxel-filter outputs, MultiMatcher jobs) would otherwise pay a capture and
+    // an instantiation - more than the launches they save - each time, and are enqueued directly instead.
+    unsigned long long pending[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool has_pending = false;
+    bool seen_before(const unsigned long long (&k)[8]) {
+        bool same = has_pending;
+        for (int i = 0; i < 8; ++i) {
+            same = same && pending[i] == k[i];
+            pending[i] = k[i];
+        }
+        has_pending = true;
+        return same;
+    }
     bool matches(const unsigned long long (&k)[8]) const {
         if (!exec) return false;
         for (int i = 0; i < 8; ++i)
@@ -270,8 +284,8 @@ __device__ __forceinline__ void walk(float qx, float qy, float qz, const TNode *
         if (link >= 0) {
             const float4 a = __ldg(&nodes[link].lo0), b = __ldg(&nodes[link].hi0);
             const float4 c = __ldg(&nodes[link].lo1), d = __ldg(&nodes[link].hi1);
-            const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
             const int l0 = __float_as_int(a.w), l1 = __float_as_int(c.w);
+            const float d0 = aabb_dist(qx, qy, qz, a, b), d1 = aabb_dist(qx, qy, qz, c, d);
             const unsigned long long k0 = nn_key(d0, __float_as_uint(b.w)), k1 = nn_key(d1, __float_as_uint(d.w));
             if (l0 < 0 && k0 < best_key) {
                 best_key = k0;

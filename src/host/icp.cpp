@@ -79,12 +79,13 @@ ICPMatcherParams::ICPMatcherParams(const std::string &config_path) {
 ICPMatcher::ICPMatcher(ICPMatcherParams params1) : params(params1) {
     this->resolution = this->params.res;
     const wavecu_icp_params c = to_c(this->params);
-    if (wavecu_icp_create(&c, pick_matcher_device(), nullptr, &this->handle) != WAVECU_OK) fail("wavecu_icp_create");
+    this->device_ = pick_matcher_device();
+    if (wavecu_icp_create(&c, this->device_, nullptr, &this->handle) != WAVECU_OK) fail("wavecu_icp_create");
 }
 
 ICPMatcher::ICPMatcher(ICPMatcher &&other) noexcept
     : Matcher<PCLPointCloudPtr>(other), params(other.params), handle(other.handle), ref(other.ref),
-      target(other.target) {
+      target(other.target), device_(other.device_) {
     other.handle = nullptr;
 }
 
@@ -110,6 +111,15 @@ void ICPMatcher::setTargetNormals(const PCLPointCloudPtr &normals) {
     const float *data = normals && !normals->points.empty() ? &normals->points[0].x : nullptr;
     if (wavecu_icp_set_target_normals(this->handle, data, normals ? normals->points.size() : 0) != WAVECU_OK)
         fail("wavecu_icp_set_target_normals");
+}
+
+void ICPMatcher::buildTarget() {
+    if (wavecu_icp_build_target(this->handle) != WAVECU_OK) fail("wavecu_icp_build_target");
+}
+
+void ICPMatcher::shareTarget(ICPMatcher *owner) {
+    if (wavecu_icp_share_target(this->handle, owner ? owner->handle : nullptr) != WAVECU_OK)
+        fail("wavecu_icp_share_target");
 }
 
 bool ICPMatcher::match() {

@@ -169,6 +169,28 @@ int main(int argc, char **argv) {
         EXPECT(got == 8 && all, "simultaneousmatching");
         std::printf("%-18s results=%d\n", "multimatcher", got);
     }
+    {  // extension: one map for all jobs (MultiMatcher::setMap), results equal to per-job targets
+        Affine3 perturb = Affine3::Identity();
+        perturb.translation() << 0.2, 0, 0;
+        PCLPointCloudPtr map = transformed(ref, perturb);
+        ICPMatcherParams params(config);
+        params.res = -1;
+        ICPMatcher single(params);
+        single.setup(ref, map);
+        const bool ok1 = single.match();
+        MultiMatcher<ICPMatcher, ICPMatcherParams> mm(3, 4, params);
+        mm.setMap(map);
+        for (int i = 0; i < 6; ++i) mm.insert(i, ref, nullptr);
+        int id = 0, got = 0;
+        Affine3 T;
+        Mat6 info;
+        while (mm.getResult(&id, &T, &info)) {
+            ++got;
+            EXPECT(ok1 && (T.matrix() - single.getResult().matrix()).norm() == 0.0, "multimatcher_map");
+        }
+        EXPECT(got == 6, "multimatcher_map");
+        std::printf("%-18s results=%d diff_vs_truth=%.3e\n", "multimatcher_map", got, (T.matrix() - perturb.matrix()).norm());
+    }
     if (argc >= 4) {  // NDTTests (tests/ndt_tests.cpp): initialization, fullResNullMatch, nullDisplacement,
                       // smallDisplacement
         const std::string ndt_config = argv[3];
