@@ -38,6 +38,12 @@ struct GicpPose {
 };
 
 constexpr int kGicpThreads = 128;
+#ifndef WCU_GICP_U
+#define WCU_GICP_U 1          // pairs per thread and trip of the cost kernel (measured: 1 and 4 equal, 2 slower)
+#endif
+#ifndef WCU_GICP_BPS
+#define WCU_GICP_BPS 4        // cost-kernel blocks per SM
+#endif
 constexpr int kCostVals = 14;  // f, g_t(3), Racc(9), pair count
 
 // one thread per Morton-sorted point; covs indexed by sorted position (9 doubles, row major)
@@ -172,25 +178,51 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *_
         v = fmin(fmax(v, -4503599627370496.0), 4503599627370496.0);
         return __double2ll_rn(v);
     };
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_src; s += gridDim.x * blockDim.x) {
-        const int j = pos[s];
-        if (j < 0) continue;
-        const float4 p = src_sorted[s];
-        const float4 q = __ldg(tgt_sorted + j);
-        const float px = xform_row(T + 0, p.x, p.y, p.z), py = xform_row(T + 4, p.x, p.y, p.z), pz = xform_row(T + 8, p.x, p.y, p.z);
-        const double r0 = (double) __fsub_rn(px, q.x), r1 = (double) __fsub_rn(py, q.y), r2 = (double) __fsub_rn(pz, q.z);
-        const double *M = mahal + 9 * (size_t) s;
-        const double t0 = (M[0] * r0 + M[1] * r1) + M[2] * r2, t1 = (M[3] * r0 + M[4] * r1) + M[5] * r2,
-                     t2 = (M[6] * r0 + M[7] * r1) + M[8] * r2;
-        acc[0] += fix((r0 * t0 + r1 * t1) + r2 * t2);
-        acc[1] += fix(t0);
-        acc[2] += fix(t1);
-        acc[3] += fix(t2);
-        const double b0 = p.x, b1 = p.y, b2 = p.z;  // base_transformation_ (identity) * p_src
-        acc[4] += fix(b0 * t0); acc[5] += fix(b0 * t1); acc[6] += fix(b0 * t2);
-        acc[7] += fix(b1 * t0); acc[8] += fix(b1 * t1); acc[9] += fix(b1 * t2);
-        acc[10] += fix(b2 * t0); acc[11] += fix(b2 * t1); acc[12] += fix(b2 * t2);
-        acc[13] += 1;
+    // Four pairs per thread and trip: the match positions first, then every load of the four pairs
+    // (source point, gathered target point, nine Mahalanobis entries) before any arithmetic - the pass is
+    // latency bound (the operands sit in L2 across the evaluations of a match), so what counts is how many
+    // independent loads a warp has in flight.
+    constexpr int kU = WCU_GICP_U;
+    const int stride = gridDim.x * blockDim.x;
+    for (int s0 = blockIdx.x * blockDim.x + threadIdx.x; s0 < n_src; s0 += kU * stride) {
+        int j[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int s = s0 + u * stride;
+            j[u] = s < n_src ? __ldg(pos + s) : -1;
+        }
+        float4 p[kU], q[kU];
+        double M[kU][9];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int s = s0 + u * stride;
+            if (j[u] >= 0) {
+                p[u] = __ldg(src_sorted + s);
+                q[u] = __ldg(tgt_sorted + j[u]);
+                const double *Mp = mahal + 9 * (size_t) s;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) M[u][k] = __ldg(Mp + k);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (j[u] < 0) continue;
+            const float px = xform_row(T + 0, p[u].x, p[u].y, p[u].z), py = xform_row(T + 4, p[u].x, p[u].y, p[u].z),
+                        pz = xform_row(T + 8, p[u].x, p[u].y, p[u].z);
+            const double r0 = (double) __fsub_rn(px, q[u].x), r1 = (double) __fsub_rn(py, q[u].y),
+                         r2 = (double) __fsub_rn(pz, q[u].z);
+            const double t0 = (M[u][0] * r0 + M[u][1] * r1) + M[u][2] * r2, t1 = (M[u][3] * r0 + M[u][4] * r1) + M[u][5] * r2,
+                         t2 = (M[u][6] * r0 + M[u][7] * r1) + M[u][8] * r2;
+            acc[0] += fix((r0 * t0 + r1 * t1) + r2 * t2);
+            acc[1] += fix(t0);
+            acc[2] += fix(t1);
+            acc[3] += fix(t2);
+            const double b0 = p[u].x, b1 = p[u].y, b2 = p[u].z;  // base_transformation_ (identity) * p_src
+            acc[4] += fix(b0 * t0); acc[5] += fix(b0 * t1); acc[6] += fix(b0 * t2);
+            acc[7] += fix(b1 * t0); acc[8] += fix(b1 * t1); acc[9] += fix(b1 * t2);
+            acc[10] += fix(b2 * t0); acc[11] += fix(b2 * t1); acc[12] += fix(b2 * t2);
+            acc[13] += 1;
+        }
     }
     __shared__ long long s_red[kGicpThreads / 32][kCostVals];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -214,9 +246,22 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *_
     if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
+    // all 128 threads add the block rows: value = thread % 16, eight interleaved chunks of blocks per value
+    // (14 threads walking ~600 rows one after the other used to cost as much as the pass itself)
+    __shared__ unsigned long long s_lo[8][16];
+    __shared__ long long s_hi[8][16];
+    {
+        const int v = threadIdx.x & 15, chunk = threadIdx.x >> 4;
+        __int128 t = 0;
+        if (v < kCostVals)
+            for (unsigned b = chunk; b < gridDim.x; b += 8) t += (__int128) __ldcg(partial + (size_t) b * kCostVals + v);
+        s_lo[chunk][v] = (unsigned long long) t;
+        s_hi[chunk][v] = (long long) (t >> 64);
+    }
+    __syncthreads();
     if (threadIdx.x < kCostVals) {
         __int128 v = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += (__int128) __ldcg(partial + (size_t) b * kCostVals + threadIdx.x);
+        for (int c = 0; c < 8; ++c) v += ((__int128) s_hi[c][threadIdx.x] << 64) + (__int128) s_lo[c][threadIdx.x];
         host_sums[threadIdx.x] = threadIdx.x == 13 ? (double) (long long) v
                                                    : acc_to_double((unsigned long long) v, (long long) (v >> 64), pose.k);
     }
@@ -789,7 +834,7 @@ int GicpHandle::match(double *T_out, int *converged_out, int *iterations_out) {
         int rc = prepare();
         if (rc) return rc;
         // cost-kernel grid: at most 16 pairs per thread (64-bit partial sums), at least four blocks per SM
-        n_blocks = (int) std::max<size_t>(148 * 4, (n_src + (size_t) kGicpThreads * 16 - 1) / ((size_t) kGicpThreads * 16));
+        n_blocks = (int) std::max<size_t>(148 * WCU_GICP_BPS, (n_src + (size_t) kGicpThreads * 16 - 1) / ((size_t) kGicpThreads * 16));
         if ((size_t) n_blocks > partial_blocks) {
             if (d_partial) WCU_CHECK(cudaFree(d_partial));
             d_partial = nullptr;

@@ -377,11 +377,19 @@ __global__ void __launch_bounds__(kNdtThreads, WCU_NDT_MINBLOCKS) ndt_derivative
     if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
-    if (threadIdx.x < kNdtVals) {
-        double v = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partial + (size_t) b * kNdtVals + threadIdx.x);
-        host_sums[threadIdx.x] = v;
+    // all 128 threads add the block rows (value = thread % 32, four interleaved chunks of blocks per value),
+    // the chunk sums are then added in a fixed order: still independent of which block came last
+    __shared__ double s_fin[4][32];
+    {
+        const int v = threadIdx.x & 31, chunk = threadIdx.x >> 5;
+        double t = 0;
+        if (v < kNdtVals)
+            for (unsigned b = chunk; b < gridDim.x; b += 4) t += __ldcg(partial + (size_t) b * kNdtVals + v);
+        s_fin[chunk][v] = t;
     }
+    __syncthreads();
+    if (threadIdx.x < kNdtVals)
+        host_sums[threadIdx.x] = (s_fin[0][threadIdx.x] + s_fin[1][threadIdx.x]) + (s_fin[2][threadIdx.x] + s_fin[3][threadIdx.x]);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
