@@ -86,30 +86,69 @@ __device__ void eig_sym3(const double A_in[9], double evals[3], double V[9]) {
     }
 }
 
-// one thread per occupied voxel (head element of its run in the sorted arrays)
-__global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict__ in, const unsigned *__restrict__ keys,
-                                                       const unsigned *__restrict__ vals,
-                                                       const int *__restrict__ pos, size_t n, NdtLeafDev *leaves) {
+// voxel slot -> first element of its run in the sorted arrays
+__global__ void __launch_bounds__(256) ndt_starts_kernel(const unsigned *__restrict__ keys, const int *__restrict__ pos,
+                                                         size_t n, int *starts) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned k = keys[i];
-    const bool head = (k != 0xffffffffu) && (i == 0 || keys[i - 1] != k);
-    if (!head) return;
+    if ((k != 0xffffffffu) && (i == 0 || keys[i - 1] != k)) starts[pos[i]] = (int) i;
+}
+
+// VoxelGridCovariance leaf statistics, one WARP per occupied voxel.  A map voxel near the sensor holds
+// tens of thousands of points: with one thread per voxel (round 1) that single serial loop of dependent
+// gathers took 8.3 ms of a 16 ms match on the 5 M-point map.  The lanes load 32 points of the run at a
+// time; the fp64 sums (mean, covariance) are per-lane partials combined by a fixed shuffle tree; the
+// fp32 centroid - which only decides which cells a point can reach, and which the parity tests compare bit
+// for bit - keeps PCL's strictly sequential summation order: one chain of adds over the lanes' values in run
+// order, fed by shuffles, so the only serial cost left is the add latency itself.
+__global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict__ in, const unsigned *__restrict__ keys,
+                                                       const unsigned *__restrict__ vals,
+                                                       const int *__restrict__ starts, int n_voxels, size_t n,
+                                                       NdtLeafDev *leaves) {
+    const int slot = (int) ((blockIdx.x * (size_t) blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= n_voxels) return;
+    const size_t start = (size_t) starts[slot];
+    const unsigned k = keys[start];
     float cx = 0.f, cy = 0.f, cz = 0.f;
-    double s[3] = {0, 0, 0}, ss[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    size_t j = i;
-    for (; j < n && keys[j] == k; ++j) {
-        const float4 p = in[vals[j]];
-        cx = __fadd_rn(cx, p.x);
-        cy = __fadd_rn(cy, p.y);
-        cz = __fadd_rn(cz, p.z);
-        const double q[3] = {p.x, p.y, p.z};
-        for (int r = 0; r < 3; ++r) {
-            s[r] += q[r];
-            for (int c = 0; c < 3; ++c) ss[3 * r + c] += q[r] * q[c];
+    double s[3] = {0, 0, 0}, ss[6] = {0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz
+    size_t cnt_total = 0;
+    for (size_t base = start;; base += 32) {
+        const size_t j = base + lane;
+        const bool mine = j < n && keys[j] == k;
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        const int cnt = __popc(m);   // the run is contiguous: the members are lanes 0 .. cnt-1
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mine) p = in[vals[j]];
+        if (mine) {
+            const double q0 = p.x, q1 = p.y, q2 = p.z;
+            s[0] += q0; s[1] += q1; s[2] += q2;
+            ss[0] += q0 * q0; ss[1] += q0 * q1; ss[2] += q0 * q2;
+            ss[3] += q1 * q1; ss[4] += q1 * q2; ss[5] += q2 * q2;
         }
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+            const float vx = __shfl_sync(0xffffffffu, p.x, l), vy = __shfl_sync(0xffffffffu, p.y, l),
+                        vz = __shfl_sync(0xffffffffu, p.z, l);
+            if (l < cnt) {
+                cx = __fadd_rn(cx, vx);
+                cy = __fadd_rn(cy, vy);
+                cz = __fadd_rn(cz, vz);
+            }
+        }
+        cnt_total += (size_t) cnt;
+        if (cnt < 32) break;
     }
-    const int cnt = (int) (j - i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) s[d] += __shfl_xor_sync(0xffffffffu, s[d], o);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) ss[d] += __shfl_xor_sync(0xffffffffu, ss[d], o);
+    }
+    if (lane != 0) return;
+    const int cnt = (int) cnt_total;
     NdtLeafDev leaf;
     leaf.voxel = (int) k;
     leaf.n = cnt;
@@ -121,10 +160,11 @@ __global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict_
     for (int d = 0; d < 3; ++d) leaf.mean[d] = s[d] / cnt;
     for (int d = 0; d < 6; ++d) leaf.icov[d] = 0;
     if (cnt >= 6) {  // min_points_per_voxel_
+        const double full[9] = {ss[0], ss[1], ss[2], ss[1], ss[3], ss[4], ss[2], ss[4], ss[5]};
         double cov[9];
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c)
-                cov[3 * r + c] = (ss[3 * r + c] - 2 * (s[r] * leaf.mean[c])) / cnt + leaf.mean[r] * leaf.mean[c];
+                cov[3 * r + c] = (full[3 * r + c] - 2 * (s[r] * leaf.mean[c])) / cnt + leaf.mean[r] * leaf.mean[c];
         for (int q = 0; q < 9; ++q) cov[q] *= (cnt - 1.0) / cnt;
         double ev[3], V[9];
         eig_sym3(cov, ev, V);
@@ -156,7 +196,7 @@ __global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict_
             }
         }
     }
-    leaves[pos[i]] = leaf;
+    leaves[slot] = leaf;
 }
 
 __device__ __forceinline__ unsigned hash_voxel(int v, unsigned mask) {
@@ -166,13 +206,17 @@ __device__ __forceinline__ unsigned hash_voxel(int v, unsigned mask) {
 }
 
 __global__ void ndt_hash_insert_kernel(const NdtLeafDev *__restrict__ leaves, int n_leaves, int *table_key,
-                                       int *table_slot, unsigned mask, int *n_valid) {
+                                       int *table_slot, unsigned mask, int *n_valid, int *dense) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n_leaves && leaves[i].valid;
     const unsigned ballot = __ballot_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_valid, __popc(ballot));
     if (!valid) return;
     const int v = leaves[i].voxel;
+    if (dense) {  // small enough grids: voxel index -> cell, one load per probe instead of a hash walk
+        dense[v] = i;
+        return;
+    }
     unsigned h = hash_voxel(v, mask);
     for (;;) {
         const int prev = atomicCAS(&table_key[h], -1, v);
@@ -205,6 +249,7 @@ __global__ void __launch_bounds__(kNdtThreads, WCU_NDT_MINBLOCKS) ndt_derivative
                                                                      const NdtLeafDev *__restrict__ leaves,
                                                                      const int *__restrict__ table_key,
                                                                      const int *__restrict__ table_slot, unsigned mask,
+                                                                     const int *__restrict__ dense,
                                                                      const __grid_constant__ NdtConsts kc,
                                                                      double *partial, unsigned *ticket,
                                                                      volatile double *host_sums, volatile int *host_seq,
@@ -241,7 +286,28 @@ __global__ void __launch_bounds__(kNdtThreads, WCU_NDT_MINBLOCKS) ndt_derivative
         // 0-4 of them hold a cell.
         int hits[27];
         int n_hits = 0;
-        {
+        if (dense) {
+            // dense voxel -> cell table: every reachable neighbour is one independent load; the cells found
+            // are then kept only if their centroid is within `res` (FLANN keeps d2 < r2), so that the
+            // arithmetic loop below runs exactly once per contributing cell
+            int slot_k[27];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) {
+                const int v0 = i0 + (k % 3) - 1, v1 = i1 + ((k / 3) % 3) - 1, v2 = i2 + (k / 9) - 1;
+                const float gx = gap[0][k % 3], gy = gap[1][(k / 3) % 3], gz = gap[2][k / 9];
+                const bool reachable = gx * gx + gy * gy + gz * gz < 1.0002f;
+                const bool inside = reachable && !(v0 < 0 || v1 < 0 || v2 < 0 || v0 >= c.grid.div_b[0] ||
+                                                   v1 >= c.grid.div_b[1] || v2 >= c.grid.div_b[2]);
+                slot_k[k] = inside ? __ldg(dense + (v0 * c.grid.mul[0] + v1 * c.grid.mul[1] + v2 * c.grid.mul[2])) : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < 27; ++k) {
+                if (slot_k[k] < 0) continue;
+                const float *cen = leaves[slot_k[k]].centroid;
+                const float dc = l2_simple(tx, ty, tz, __ldg(cen), __ldg(cen + 1), __ldg(cen + 2));
+                if (dc < c.r2) hits[n_hits++] = slot_k[k];
+            }
+        } else {
             int first_key[27], vox_id[27];
             unsigned first_h[27];
 #pragma unroll
@@ -269,7 +335,10 @@ __global__ void __launch_bounds__(kNdtThreads, WCU_NDT_MINBLOCKS) ndt_derivative
                     h = (h + 1) & mask;
                     key = __ldg(table_key + h);
                 }
-                if (slot >= 0) hits[n_hits++] = slot;
+                if (slot < 0) continue;
+                const float *cen = leaves[slot].centroid;
+                const float dc = l2_simple(tx, ty, tz, __ldg(cen), __ldg(cen + 1), __ldg(cen + 2));
+                if (dc < c.r2) hits[n_hits++] = slot;
             }
         }
         // Per-hit arithmetic, written out for the structure of the problem: the translation columns of the
@@ -282,8 +351,6 @@ __global__ void __launch_bounds__(kNdtThreads, WCU_NDT_MINBLOCKS) ndt_derivative
         for (int hit = 0; hit < n_hits; ++hit) {
             const int slot = hits[hit];
             const NdtLeafDev &cell = leaves[slot];
-            const float dc = l2_simple(tx, ty, tz, cell.centroid[0], cell.centroid[1], cell.centroid[2]);
-            if (!(dc < c.r2)) continue;
             if (!have_point_terms) {  // computePointDerivatives, once per point
                 have_point_terms = true;
                 J3[0] = 0.0;            J3[1] = dot3(x, c.ja); J3[2] = dot3(x, c.jb);
@@ -581,6 +648,12 @@ struct NdtHandle {
     int n_cells = -1;      // of which normal-distribution cells (>= 6 points, usable covariance); -1: not read yet
     int *d_n_valid = nullptr;
     int *d_table_key = nullptr, *d_table_slot = nullptr;
+    int *d_starts = nullptr;         // voxel slot -> first element of its run
+    size_t starts_cap = 0;
+    int *d_dense = nullptr;          // voxel index -> cell for grids of up to kDenseMax voxels, else nullptr (hash)
+    size_t dense_cap = 0;
+    bool use_dense = false;
+    static constexpr long long kDenseMax = 64ll << 20;   // 256 MB of ints
     size_t table_cap = 0;
     unsigned table_mask = 0;
     float resolution = 1.f;
@@ -670,13 +743,34 @@ struct NdtHandle {
         }
         table_mask = (unsigned) (slots - 1);
         WCU_CHECK(cudaMemsetAsync(d_table_key, 0xff, slots * sizeof(int), stream));
-        ndt_leaf_kernel<<<(unsigned) ((n_tgt + 255) / 256), 256, 0, stream>>>(d_tgt, vox.d_keys, vox.d_vals, vox.d_pos,
-                                                                              n_tgt, d_leaves);
+        const long long n_vox = (long long) grid.div_b[0] * grid.div_b[1] * grid.div_b[2];
+        use_dense = n_vox > 0 && n_vox <= kDenseMax;
+        if (use_dense) {
+            if ((size_t) n_vox > dense_cap) {
+                if (d_dense) WCU_CHECK(cudaFree(d_dense));
+                d_dense = nullptr;
+                WCU_CHECK(cudaMalloc((void **) &d_dense, (size_t) n_vox * sizeof(int)));
+                dense_cap = (size_t) n_vox;
+            }
+            WCU_CHECK(cudaMemsetAsync(d_dense, 0xff, (size_t) n_vox * sizeof(int), stream));
+        }
+        if ((size_t) n_leaves > starts_cap) {
+            if (d_starts) WCU_CHECK(cudaFree(d_starts));
+            d_starts = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &d_starts, ((size_t) n_leaves + 64) * sizeof(int)));
+            starts_cap = (size_t) n_leaves + 64;
+        }
+        ndt_starts_kernel<<<(unsigned) ((n_tgt + 255) / 256), 256, 0, stream>>>(vox.d_keys, vox.d_pos, n_tgt, d_starts);
+        if (n_leaves)
+            ndt_leaf_kernel<<<(unsigned) (((size_t) n_leaves * 32 + 255) / 256), 256, 0, stream>>>(
+                d_tgt, vox.d_keys, vox.d_vals, d_starts, n_leaves, n_tgt, d_leaves);
+        ++launches;
         WCU_CHECK(cudaMemsetAsync(d_n_valid, 0, sizeof(int), stream));
         n_cells = -1;
         if (n_leaves)
             ndt_hash_insert_kernel<<<(n_leaves + 255) / 256, 256, 0, stream>>>(d_leaves, n_leaves, d_table_key,
-                                                                               d_table_slot, table_mask, d_n_valid);
+                                                                               d_table_slot, table_mask, d_n_valid,
+                                                                               use_dense ? d_dense : nullptr);
         launches += 2;
         WCU_CHECK(cudaGetLastError());
         grid_ok = true;
@@ -715,7 +809,8 @@ struct NdtHandle {
             WCU_CHECK(cudaEventRecord(ev0, stream));
         }
         ndt_derivative_kernel<<<n_blocks, kNdtThreads, 0, stream>>>(src_sorted.d_sorted, (int) n_src, d_leaves, d_table_key,
-                                                                     d_table_slot, table_mask, c, d_partial, d_ticket,
+                                                                     d_table_slot, table_mask, use_dense ? d_dense : nullptr, c,
+                                                                     d_partial, d_ticket,
                                                                      h_sums, h_seq, seq);
         if (profiling) WCU_CHECK(cudaEventRecord(ev1, stream));
         ++launches;
@@ -880,6 +975,8 @@ struct NdtHandle {
         cudaSetDevice(device);
         vox.release();
         src_sorted.release();
+        if (d_dense) cudaFree(d_dense);
+        if (d_starts) cudaFree(d_starts);
         for (void *p : {(void *) d_src, (void *) d_tgt, (void *) d_leaves, (void *) d_table_key, (void *) d_table_slot,
                         (void *) d_partial})
             if (p) cudaFree(p);
