@@ -41,10 +41,11 @@ constexpr int kGicpThreads = 128;
 #ifndef WCU_GICP_U
 #define WCU_GICP_U 1          // pairs per thread and trip of the cost kernel (measured: 1 and 4 equal, 2 slower)
 #endif
-#ifndef WCU_GICP_BPS
-#define WCU_GICP_BPS 4        // cost-kernel blocks per SM
+#ifndef WCU_GICP_PPT
+#define WCU_GICP_PPT 4        // pairs per thread of the cost kernel (sets its grid; measured 1 / 2 / 4 / 8: 29.8 / 24.7 / 22.2 / 24.1 us)
 #endif
 constexpr int kCostVals = 14;  // f, g_t(3), Racc(9), pair count
+constexpr int kCostSlots = 16; // accumulator replicas of the cost kernel (atomic contention spreading)
 
 // one thread per Morton-sorted point; covs indexed by sorted position (9 doubles, row major)
 __global__ void __launch_bounds__(kGicpThreads) gicp_cov_kernel(NnIndex ix, int n, int k, double eps, double *covs) {
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_corr_kernel(const float4 *_
                                                                  NnIndex tgt, const double *__restrict__ cov_src,
                                                                  const double *__restrict__ cov_tgt,
                                                                  const GicpIterConsts *__restrict__ kc, int *pos,
-                                                                 double *mahal) {
+                                                                 double *mahal, size_t ld) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_src) return;
     const float4 p = src_sorted[s];
@@ -141,24 +142,26 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_corr_kernel(const float4 *_
     const double a = t[0], b = t[1], c = t[2], d = t[3], e = t[4], f = t[5], g = t[6], h = t[7], i = t[8];
     const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
     const double id = 1.0 / det;
-    double *out = mahal + 9 * (size_t) s;
-    out[0] = (e * i - f * h) * id;
-    out[1] = (c * h - b * i) * id;
-    out[2] = (b * f - c * e) * id;
-    out[3] = (f * g - d * i) * id;
-    out[4] = (a * i - c * g) * id;
-    out[5] = (c * d - a * f) * id;
-    out[6] = (d * h - e * g) * id;
-    out[7] = (b * g - a * h) * id;
-    out[8] = (a * e - b * d) * id;
+    // stored entry-major (nine arrays of `ld` doubles): the cost kernel's loads of one entry are then
+    // contiguous across the lanes of a warp instead of 72 bytes apart
+    double *out = mahal + (size_t) s;
+    out[0 * ld] = (e * i - f * h) * id;
+    out[1 * ld] = (c * h - b * i) * id;
+    out[2 * ld] = (b * f - c * e) * id;
+    out[3 * ld] = (f * g - d * i) * id;
+    out[4 * ld] = (a * i - c * g) * id;
+    out[5 * ld] = (c * d - a * f) * id;
+    out[6 * ld] = (d * h - e * g) * id;
+    out[7 * ld] = (b * g - a * h) * id;
+    out[8 * ld] = (a * e - b * d) * id;
 }
 
 // f, g_t, Racc of OptimizationFunctorWithIndices::fdf for the transform T (fp32)
 __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *__restrict__ src_sorted, int n_src,
                                                                  const float4 *__restrict__ tgt_sorted,
                                                                  const int *__restrict__ pos,
-                                                                 const double *__restrict__ mahal, GicpPose pose,
-                                                                 long long *partial, unsigned *ticket,
+                                                                 const double *__restrict__ mahal, size_t ld, GicpPose pose,
+                                                                 Acc128 *acc128, unsigned *ticket,
                                                                  volatile double *host_sums, volatile int *host_seq,
                                                                  int seq) {
     __shared__ float T[12];
@@ -199,9 +202,9 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *_
             if (j[u] >= 0) {
                 p[u] = __ldg(src_sorted + s);
                 q[u] = __ldg(tgt_sorted + j[u]);
-                const double *Mp = mahal + 9 * (size_t) s;
+                const double *Mp = mahal + (size_t) s;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) M[u][k] = __ldg(Mp + k);
+                for (int k = 0; k < 9; ++k) M[u][k] = __ldg(Mp + (size_t) k * ld);
             }
         }
 #pragma unroll
@@ -233,35 +236,32 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_cost_kernel(const float4 *_
         if (lane == 0) s_red[warp][i] = v;
     }
     __syncthreads();
+    // block totals go to one of kCostSlots replicas of 128-bit accumulators (64-bit atomics, the carry
+    // derived from what each add observed - exact and order independent); the last block to arrive adds the
+    // replicas, clears them for the next evaluation and hands the 14 sums to the host through mapped memory:
+    // one launch and no copy per BFGS evaluation, of which a match makes several hundred.
     if (threadIdx.x < kCostVals) {
         long long v = 0;
         for (int w = 0; w < kGicpThreads / 32; ++w) v += s_red[w][threadIdx.x];
-        partial[(size_t) blockIdx.x * kCostVals + threadIdx.x] = v;
+        if (v != 0) atomic_add128(acc128 + (blockIdx.x % kCostSlots) * 16 + threadIdx.x, (unsigned long long) v, v < 0 ? -1LL : 0LL);
     }
-    // The last block to arrive adds the block rows and hands the 14 sums to the host through mapped
-    // memory: one launch and no copy per BFGS evaluation, of which a match makes several hundred.
     __shared__ bool s_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
-    // all 128 threads add the block rows: value = thread % 16, eight interleaved chunks of blocks per value
-    // (14 threads walking ~600 rows one after the other used to cost as much as the pass itself)
-    __shared__ unsigned long long s_lo[8][16];
-    __shared__ long long s_hi[8][16];
-    {
-        const int v = threadIdx.x & 15, chunk = threadIdx.x >> 4;
-        __int128 t = 0;
-        if (v < kCostVals)
-            for (unsigned b = chunk; b < gridDim.x; b += 8) t += (__int128) __ldcg(partial + (size_t) b * kCostVals + v);
-        s_lo[chunk][v] = (unsigned long long) t;
-        s_hi[chunk][v] = (long long) (t >> 64);
-    }
-    __syncthreads();
+    __threadfence();
     if (threadIdx.x < kCostVals) {
         __int128 v = 0;
-        for (int c = 0; c < 8; ++c) v += ((__int128) s_hi[c][threadIdx.x] << 64) + (__int128) s_lo[c][threadIdx.x];
+        for (int sl = 0; sl < kCostSlots; ++sl) {
+            Acc128 &c = acc128[sl * 16 + threadIdx.x];
+            const unsigned long long lo = __ldcg(&c.lo);
+            const long long hi = __ldcg(&c.hi);
+            v += ((__int128) hi << 64) + (__int128) lo;
+            c.lo = 0;
+            c.hi = 0;
+        }
         host_sums[threadIdx.x] = threadIdx.x == 13 ? (double) (long long) v
                                                    : acc_to_double((unsigned long long) v, (long long) (v >> 64), pose.k);
     }
@@ -363,8 +363,7 @@ struct GicpHandle {
     size_t src_cap = 0, tgt_cap = 0;
     bool cov_src_ok = false, cov_tgt_ok = false;
     GicpIterConsts *d_consts = nullptr;
-    long long *d_partial = nullptr;   // per-block fixed-point partial sums of the cost kernel
-    size_t partial_blocks = 0;
+    Acc128 *d_partial = nullptr;      // kCostSlots x 16 fixed-point accumulators of the cost kernel
     double *h_sums = nullptr;         // mapped host memory
     int sum_k = 28;                   // fixed-point exponent of the cost sums of the current match
     unsigned *d_ticket = nullptr;
@@ -499,7 +498,7 @@ struct GicpHandle {
             WCU_CHECK(cudaEventRecord(ev0, stream));
         }
         gicp_cost_kernel<<<n_blocks, kGicpThreads, 0, stream>>>(src.cloud.d_sorted, (int) src.cloud.n, tgt.cloud.d_sorted,
-                                                                d_pos, d_mahal, pose, d_partial, d_ticket, h_sums,
+                                                                d_pos, d_mahal, src_cap, pose, d_partial, d_ticket, h_sums,
                                                                 h_seq, seq);
         if (profiling) WCU_CHECK(cudaEventRecord(ev1, stream));
         ++launches;
@@ -833,13 +832,11 @@ int GicpHandle::match(double *T_out, int *converged_out, int *iterations_out) {
     if (n_src && n_tgt) {
         int rc = prepare();
         if (rc) return rc;
-        // cost-kernel grid: at most 16 pairs per thread (64-bit partial sums), at least four blocks per SM
-        n_blocks = (int) std::max<size_t>(148 * WCU_GICP_BPS, (n_src + (size_t) kGicpThreads * 16 - 1) / ((size_t) kGicpThreads * 16));
-        if ((size_t) n_blocks > partial_blocks) {
-            if (d_partial) WCU_CHECK(cudaFree(d_partial));
-            d_partial = nullptr;
-            WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(long long) * kCostVals * (size_t) n_blocks));
-            partial_blocks = (size_t) n_blocks;
+        // cost-kernel grid: WCU_GICP_PPT pairs per thread
+        n_blocks = (int) std::max<size_t>(1, (n_src + (size_t) kGicpThreads * WCU_GICP_PPT - 1) / ((size_t) kGicpThreads * WCU_GICP_PPT));
+        if (!d_partial) {
+            WCU_CHECK(cudaMalloc((void **) &d_partial, sizeof(Acc128) * kCostSlots * 16));
+            WCU_CHECK(cudaMemsetAsync(d_partial, 0, sizeof(Acc128) * kCostSlots * 16, stream));
         }
         {   // fixed-point exponent of the cost sums from the source extent (oracle: gicp_sum_exponent)
             unsigned bb[6];
@@ -873,7 +870,7 @@ int GicpHandle::match(double *T_out, int *converged_out, int *iterations_out) {
             c.thr = thr;
             WCU_CHECK(cudaMemcpyAsync(d_consts, &c, sizeof c, cudaMemcpyHostToDevice, stream));
             gicp_corr_kernel<<<(unsigned) ((n_src + kGicpThreads - 1) / kGicpThreads), kGicpThreads, 0, stream>>>(
-                src.cloud.d_sorted, (int) n_src, tgt.index(), d_cov_src, d_cov_tgt, d_consts, d_pos, d_mahal);
+                src.cloud.d_sorted, (int) n_src, tgt.index(), d_cov_src, d_cov_tgt, d_consts, d_pos, d_mahal, src_cap);
             ++launches;
             std::memcpy(previous, transformation, sizeof previous);
             // the pair count comes with the first cost evaluation (slot 13)
