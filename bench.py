@@ -10,8 +10,9 @@ Velodyne-style scan against a 1 M-point scan of the same scene (generator: libwa
 SURVEY.md 8(d)), search-structure build included.  Metric: point-pairs/s = sum over ICP iterations of
 source points queried / time.  N > 1: the batch-of-scans case - every rank matches its own scan pair
 (weak scaling), no data-path collective, results gathered once after the timed steps.  The line also
-carries a `batch256` sub-record (configs[4]: 256 independent 200 k-point scan-to-map alignments sharded
-over the ranks through the C batch API, map indexed once per GPU, one all-gather of the records).
+carries sub-records: `batch256` (configs[4]: 256 independent 200 k-point scan-to-map alignments sharded
+over the ranks through the C batch API, map indexed once per GPU, one all-gather of the records) and, at N = 1,
+`gicp500k` / `ndt1m5m` (configs[2] / [3], the lines of their own --workload runs with fewer steps).
 
 `value`    inputs already resident in HBM, timed with CUDA events on the launch stream.
 `e2e`      the same match through the public host API from pinned host clouds (H2D copies and the
@@ -394,6 +395,12 @@ def run_ours(args):
     sub = None
     if not args.no_batch:
         sub = batch256(args, W, batch, torch, dist, rank, local_rank, world, dev, steps=max(1, min(args.steps, 3)))
+    # BASELINE configs[2] and [3] ride along as sub-records of the single-GPU line (the scaling runs keep to the
+    # headline and the batch): same keys as their own --workload lines, fewer steps
+    sub_gicp = sub_ndt = None
+    if world == 1 and not args.no_batch:
+        sub_gicp = gicp_record(args, W, batch, torch, dist, rank, local_rank, world, dev, 3, 3)
+        sub_ndt = ndt_record(args, W, batch, torch, dist, rank, local_rank, world, dev, 3, 3)
 
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -440,7 +447,7 @@ def run_ours(args):
                                       "icp_iterations": prof_run["iters"]},
             "results_gathered": {"ranks": int(np.isfinite(table[:, 0]).sum()),
                                  "all_converged": bool(np.nansum(table[:, 16]) == world)},
-            "batch256": sub,
+            "batch256": sub, "gicp500k": sub_gicp, "ndt1m5m": sub_ndt,
         }
         print(json.dumps(line))
     finish_dist(dist, world)
@@ -569,6 +576,13 @@ def run_reference_gicp(args):
 
 
 def run_gicp(args, W, batch, torch, dist, rank, local_rank, world, dev):
+    rec = gicp_record(args, W, batch, torch, dist, rank, local_rank, world, dev, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(rec))
+    return 0
+
+
+def gicp_record(args, W, batch, torch, dist, rank, local_rank, world, dev, steps, warmup):
     from libwave_b200 import synth
     src, tgt = synth.scan_pair(GICP_N, scan_id=None if rank == 0 else rank)
     xs, xt = synth.to_xyzw(src), synth.to_xyzw(tgt)
@@ -618,10 +632,10 @@ def run_gicp(args, W, batch, torch, dist, rank, local_rank, world, dev):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.mark_start()
-    dev_run = timed(step_device, args.steps, args.warmup)
-    e2e_run = timed(step_host, args.steps, args.warmup)
+    dev_run = timed(step_device, steps, warmup)
+    e2e_run = timed(step_host, steps, warmup)
     m.set_profiling(True)
-    prof = timed(step_device, args.steps, 1)
+    prof = timed(step_device, steps, 1)
     m.set_profiling(False)
     if sampler:
         sampler.mark_end()
@@ -647,14 +661,14 @@ def run_gicp(args, W, batch, torch, dist, rank, local_rank, world, dev):
                                           "note": "the restated PCL algorithm itself stops this far from the truth on "
                                                   "this pair (k = 10 neighbourhoods of a 7813-step ring are line "
                                                   "segments); 1.6 cm / 0.6 cm at 10k / 200k points"}}
-        print(json.dumps({
+        return {
             "metric": GICP_METRIC, "value": dev_run["pairs_all"] / (dev_run["total_ms"] * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_run["total_ms"] / args.steps,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_run["total_ms"] / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": gicp_config(),
             "e2e": {"value": e2e_run["pairs_all"] / (e2e_run["total_ms"] * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(2 * 16 * n), "d2h_bytes_per_step": 128,
-                    "ms_per_step": e2e_run["total_ms"] / args.steps},
+                    "ms_per_step": e2e_run["total_ms"] / steps},
             "gpu_launches": int(dev_run["launches"]), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "gicp_cost_kernel (f, gradient and rotation accumulator of one BFGS "
                          "evaluation; the Mahalanobis matrices are kept in fp64: 72 B/pair read, 60 B/pair algorithmic)",
@@ -662,8 +676,8 @@ def run_gicp(args, W, batch, torch, dist, rank, local_rank, world, dev):
                          "traffic": traffic_of("gicp_cost_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "mean_launch_ms": mean_ms, "launches_timed": int(prof["cost_n"])},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
-            "parity": parity}))
-    return 0
+            "parity": parity}
+    return None
 
 
 # ================================================================================================
@@ -714,6 +728,13 @@ def run_reference_ndt(args):
 
 
 def run_ndt(args, W, batch, torch, dist, rank, local_rank, world, dev):
+    rec = ndt_record(args, W, batch, torch, dist, rank, local_rank, world, dev, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(rec))
+    return 0
+
+
+def ndt_record(args, W, batch, torch, dist, rank, local_rank, world, dev, steps, warmup):
     from libwave_b200 import synth
     scan, big = ndt_clouds(rank)
     xs, xt = synth.to_xyzw(scan), synth.to_xyzw(big)
@@ -763,10 +784,10 @@ def run_ndt(args, W, batch, torch, dist, rank, local_rank, world, dev):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.mark_start()
-    dev_run = timed(step_device, args.steps, args.warmup)
-    e2e_run = timed(step_host, args.steps, args.warmup)
+    dev_run = timed(step_device, steps, warmup)
+    e2e_run = timed(step_host, steps, warmup)
     m.set_profiling(True)
-    prof = timed(step_device, args.steps, 1)
+    prof = timed(step_device, steps, 1)
     m.set_profiling(False)
     if sampler:
         sampler.mark_end()
@@ -789,14 +810,14 @@ def run_ndt(args, W, batch, torch, dist, rank, local_rank, world, dev):
                       "vs_oracle": {"translation_m": dt_o, "rotation_rad": dr_o,
                                     "within_1e-4m_1e-5rad": bool(dt_o < 1e-4 and dr_o < 1e-5)},
                       "vs_ground_truth": {"translation_error_m": dt_true, "rotation_error_rad": dr_true}}
-        print(json.dumps({
+        return {
             "metric": NDT_METRIC, "value": dev_run["pairs_all"] / (dev_run["total_ms"] * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_run["total_ms"] / args.steps,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dev_run["total_ms"] / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(ndt_config(), n_target=int(nt), n_cells=int(st["n_cells"])),
             "e2e": {"value": e2e_run["pairs_all"] / (e2e_run["total_ms"] * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(16 * (n + nt)), "d2h_bytes_per_step": 128,
-                    "ms_per_step": e2e_run["total_ms"] / args.steps},
+                    "ms_per_step": e2e_run["total_ms"] / steps},
             "gpu_launches": int(dev_run["launches"]), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "ndt_derivative_kernel (score, gradient and Hessian over the 27-voxel "
                          "neighbourhood of every transformed source point)",
@@ -804,8 +825,8 @@ def run_ndt(args, W, batch, torch, dist, rank, local_rank, world, dev):
                          "traffic": traffic_of("ndt_derivative_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "mean_launch_ms": mean_ms, "launches_timed": int(prof["der_n"])},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
-            "parity": parity, "accuracy": {"translation_error_m": dt_true, "rotation_error_rad": dr_true}}))
-    return 0
+            "parity": parity, "accuracy": {"translation_error_m": dt_true, "rotation_error_rad": dr_true}}
+    return None
 
 
 def main():
@@ -815,7 +836,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline and parity legs (profiling runs)")
-    ap.add_argument("--no-batch", action="store_true", help="icp1m: omit the batch256 sub-record")
+    ap.add_argument("--no-batch", action="store_true", help="icp1m: omit the batch256 / gicp500k / ndt1m5m sub-records")
     ap.add_argument("--workload", default="icp1m", choices=["icp1m", "batch256", "gicp500k", "ndt1m5m"],
                     help="icp1m: BASELINE.json configs[1] (default, the headline, with a batch256 sub-record); "
                          "batch256: configs[4] alone; gicp500k: configs[2]; ndt1m5m: configs[3]")
