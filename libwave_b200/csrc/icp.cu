@@ -87,6 +87,7 @@ __global__ void setup_kernel(SetupArgs a) {
     st.converged = 0;
     st.state = WAVECU_CONV_NOT_CONVERGED;
     st.n_corr = 0;
+    st.pad = 0;
     st.fb_total = 0;
 }
 
@@ -396,6 +397,7 @@ int IcpHandle::ensure_iter_buffers(size_t n_src_pad, int max_iter) {
         if (d_trace) WCU_CHECK(cudaFree(d_trace));
         d_trace = nullptr;
         WCU_CHECK(cudaMalloc((void **) &d_trace, sizeof(TraceRow) * (size_t) max_iter));
+        WCU_CHECK(cudaMemsetAsync(d_trace, 0, sizeof(TraceRow) * (size_t) max_iter, stream));   // rows of launches past convergence are read back unwritten
         trace_cap = max_iter;
     }
     return WAVECU_OK;

@@ -482,6 +482,7 @@ __device__ __noinline__ void solve_block(const SolveArgs &a) {
         TraceRow &row = a.trace[it - 1];
         row.mse = mse;
         row.n_corr = (int) n;
+        row.pad = 0;
         for (int i = 0; i < 16; ++i) row.T[i] = T[i];
     }
 
