@@ -95,15 +95,23 @@ __global__ void __launch_bounds__(256) ndt_starts_kernel(const unsigned *__restr
     if ((k != 0xffffffffu) && (i == 0 || keys[i - 1] != k)) starts[pos[i]] = (int) i;
 }
 
+// points in voxel-sorted order (pcl's index_vector after its sort): the leaf kernel below then streams
+// contiguous memory instead of chasing vals[] -> in[] for every point
+__global__ void __launch_bounds__(256) ndt_gather_kernel(const float4 *__restrict__ in, const unsigned *__restrict__ keys,
+                                                         const unsigned *__restrict__ vals, size_t n, float4 *out) {
+    const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (keys[i] != 0xffffffffu) out[i] = in[vals[i]];
+}
+
 // VoxelGridCovariance leaf statistics, one WARP per occupied voxel.  A map voxel near the sensor holds
 // tens of thousands of points: with one thread per voxel (round 1) that single serial loop of dependent
-// gathers took 8.3 ms of a 16 ms match on the 5 M-point map.  The lanes load 32 points of the run at a
-// time; the fp64 sums (mean, covariance) are per-lane partials combined by a fixed shuffle tree; the
-// fp32 centroid - which only decides which cells a point can reach, and which the parity tests compare bit
-// for bit - keeps PCL's strictly sequential summation order: one chain of adds over the lanes' values in run
-// order, fed by shuffles, so the only serial cost left is the add latency itself.
-__global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict__ in, const unsigned *__restrict__ keys,
-                                                       const unsigned *__restrict__ vals,
+// gathers took 8.3 ms of a 16 ms match on the 5 M-point map.  The lanes read 4 x 32 consecutive points of
+// the run per trip; the fp64 sums (mean, covariance) are per-lane partials combined by a fixed shuffle
+// tree; the fp32 centroid - which only decides which cells a point can reach, and which the parity tests
+// compare bit for bit - keeps PCL's strictly sequential summation order: one chain of adds over the lanes'
+// values in run order, fed by shuffles, so the only serial cost left is the add latency itself.
+__global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict__ pts, const unsigned *__restrict__ keys,
                                                        const int *__restrict__ starts, int n_voxels, size_t n,
                                                        NdtLeafDev *leaves) {
     const int slot = (int) ((blockIdx.x * (size_t) blockDim.x + threadIdx.x) >> 5);
@@ -111,34 +119,46 @@ __global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict_
     if (slot >= n_voxels) return;
     const size_t start = (size_t) starts[slot];
     const unsigned k = keys[start];
+    // end of the run: the start of the next voxel's, or the first element that is not this voxel's
+    size_t end;
+    if (slot + 1 < n_voxels) end = (size_t) starts[slot + 1];
+    else {
+        end = start;
+        while (end < n && keys[end] == k) ++end;   // last voxel only; lanes agree
+    }
     float cx = 0.f, cy = 0.f, cz = 0.f;
     double s[3] = {0, 0, 0}, ss[6] = {0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz
-    size_t cnt_total = 0;
-    for (size_t base = start;; base += 32) {
-        const size_t j = base + lane;
-        const bool mine = j < n && keys[j] == k;
-        const unsigned m = __ballot_sync(0xffffffffu, mine);
-        const int cnt = __popc(m);   // the run is contiguous: the members are lanes 0 .. cnt-1
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (mine) p = in[vals[j]];
-        if (mine) {
-            const double q0 = p.x, q1 = p.y, q2 = p.z;
-            s[0] += q0; s[1] += q1; s[2] += q2;
-            ss[0] += q0 * q0; ss[1] += q0 * q1; ss[2] += q0 * q2;
-            ss[3] += q1 * q1; ss[4] += q1 * q2; ss[5] += q2 * q2;
+    const size_t cnt_total = end - start;
+    constexpr int kTrip = 4;
+    for (size_t base = start; base < end; base += 32 * kTrip) {
+        float4 p[kTrip];
+#pragma unroll
+        for (int u = 0; u < kTrip; ++u) {
+            const size_t j = base + (size_t) u * 32 + lane;
+            p[u] = j < end ? pts[j] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int l = 0; l < 32; ++l) {
-            const float vx = __shfl_sync(0xffffffffu, p.x, l), vy = __shfl_sync(0xffffffffu, p.y, l),
-                        vz = __shfl_sync(0xffffffffu, p.z, l);
-            if (l < cnt) {
-                cx = __fadd_rn(cx, vx);
-                cy = __fadd_rn(cy, vy);
-                cz = __fadd_rn(cz, vz);
+        for (int u = 0; u < kTrip; ++u) {
+            const size_t j0 = base + (size_t) u * 32;
+            if (j0 >= end) break;
+            const int cnt = (int) (end - j0 < 32 ? end - j0 : 32);   // members are lanes 0 .. cnt-1
+            if (lane < cnt) {
+                const double q0 = p[u].x, q1 = p[u].y, q2 = p[u].z;
+                s[0] += q0; s[1] += q1; s[2] += q2;
+                ss[0] += q0 * q0; ss[1] += q0 * q1; ss[2] += q0 * q2;
+                ss[3] += q1 * q1; ss[4] += q1 * q2; ss[5] += q2 * q2;
+            }
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const float vx = __shfl_sync(0xffffffffu, p[u].x, l), vy = __shfl_sync(0xffffffffu, p[u].y, l),
+                            vz = __shfl_sync(0xffffffffu, p[u].z, l);
+                if (l < cnt) {
+                    cx = __fadd_rn(cx, vx);
+                    cy = __fadd_rn(cy, vy);
+                    cz = __fadd_rn(cz, vz);
+                }
             }
         }
-        cnt_total += (size_t) cnt;
-        if (cnt < 32) break;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -148,15 +168,30 @@ __global__ void __launch_bounds__(256) ndt_leaf_kernel(const float4 *__restrict_
         for (int d = 0; d < 6; ++d) ss[d] += __shfl_xor_sync(0xffffffffu, ss[d], o);
     }
     if (lane != 0) return;
-    const int cnt = (int) cnt_total;
+    // raw sums; ndt_leaf_finish_kernel (one thread per voxel, all lanes busy) turns them into the statistics
     NdtLeafDev leaf;
     leaf.voxel = (int) k;
-    leaf.n = cnt;
+    leaf.n = (int) cnt_total;
     leaf.valid = 0;
+    leaf.centroid[0] = cx; leaf.centroid[1] = cy; leaf.centroid[2] = cz;
+    for (int d = 0; d < 3; ++d) leaf.mean[d] = s[d];
+    for (int d = 0; d < 6; ++d) leaf.icov[d] = ss[d];
+    leaves[slot] = leaf;
+}
+
+// mean, regularised covariance and its inverse of every voxel from the sums above (VoxelGridCovariance:
+// >= 6 points, eigenvalue floor 0.01 * largest)
+__global__ void __launch_bounds__(128) ndt_leaf_finish_kernel(NdtLeafDev *leaves, int n_voxels) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_voxels) return;
+    NdtLeafDev leaf = leaves[slot];
+    const int cnt = leaf.n;
+    const double s[3] = {leaf.mean[0], leaf.mean[1], leaf.mean[2]};
+    const double ss[6] = {leaf.icov[0], leaf.icov[1], leaf.icov[2], leaf.icov[3], leaf.icov[4], leaf.icov[5]};
     const float fn = (float) cnt;
-    leaf.centroid[0] = __fdiv_rn(cx, fn);
-    leaf.centroid[1] = __fdiv_rn(cy, fn);
-    leaf.centroid[2] = __fdiv_rn(cz, fn);
+    leaf.centroid[0] = __fdiv_rn(leaf.centroid[0], fn);
+    leaf.centroid[1] = __fdiv_rn(leaf.centroid[1], fn);
+    leaf.centroid[2] = __fdiv_rn(leaf.centroid[2], fn);
     for (int d = 0; d < 3; ++d) leaf.mean[d] = s[d] / cnt;
     for (int d = 0; d < 6; ++d) leaf.icov[d] = 0;
     if (cnt >= 6) {  // min_points_per_voxel_
@@ -648,6 +683,8 @@ struct NdtHandle {
     int n_cells = -1;      // of which normal-distribution cells (>= 6 points, usable covariance); -1: not read yet
     int *d_n_valid = nullptr;
     int *d_table_key = nullptr, *d_table_slot = nullptr;
+    float4 *d_gathered = nullptr;    // target points in voxel-sorted order
+    size_t gathered_cap = 0;
     int *d_starts = nullptr;         // voxel slot -> first element of its run
     size_t starts_cap = 0;
     int *d_dense = nullptr;          // voxel index -> cell for grids of up to kDenseMax voxels, else nullptr (hash)
@@ -761,10 +798,20 @@ struct NdtHandle {
             starts_cap = (size_t) n_leaves + 64;
         }
         ndt_starts_kernel<<<(unsigned) ((n_tgt + 255) / 256), 256, 0, stream>>>(vox.d_keys, vox.d_pos, n_tgt, d_starts);
+        if (n_tgt > gathered_cap) {
+            if (d_gathered) WCU_CHECK(cudaFree(d_gathered));
+            d_gathered = nullptr;
+            WCU_CHECK(cudaMalloc((void **) &d_gathered, (n_tgt + 64) * sizeof(float4)));
+            gathered_cap = n_tgt + 64;
+        }
+        ndt_gather_kernel<<<(unsigned) ((n_tgt + 255) / 256), 256, 0, stream>>>(d_tgt, vox.d_keys, vox.d_vals, n_tgt,
+                                                                                d_gathered);
+        ++launches;
         if (n_leaves)
             ndt_leaf_kernel<<<(unsigned) (((size_t) n_leaves * 32 + 255) / 256), 256, 0, stream>>>(
-                d_tgt, vox.d_keys, vox.d_vals, d_starts, n_leaves, n_tgt, d_leaves);
-        ++launches;
+                d_gathered, vox.d_keys, d_starts, n_leaves, n_tgt, d_leaves);
+        if (n_leaves) ndt_leaf_finish_kernel<<<(unsigned) ((n_leaves + 127) / 128), 128, 0, stream>>>(d_leaves, n_leaves);
+        launches += 2;
         WCU_CHECK(cudaMemsetAsync(d_n_valid, 0, sizeof(int), stream));
         n_cells = -1;
         if (n_leaves)
@@ -977,6 +1024,7 @@ struct NdtHandle {
         src_sorted.release();
         if (d_dense) cudaFree(d_dense);
         if (d_starts) cudaFree(d_starts);
+        if (d_gathered) cudaFree(d_gathered);
         for (void *p : {(void *) d_src, (void *) d_tgt, (void *) d_leaves, (void *) d_table_key, (void *) d_table_slot,
                         (void *) d_partial})
             if (p) cudaFree(p);
