@@ -36,10 +36,15 @@ __global__ void voxel_head_kernel(const unsigned *__restrict__ keys, size_t n, i
     flags[i] = (k != 0xffffffffu && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
 }
 
-// one thread per voxel: fp32 sums in ascending cloud index (the sort is stable), centroid = sum / n
+// fp32 sums in ascending cloud index (the sort is stable), centroid = sum / n.  One thread per voxel for
+// runs of up to kShortRun points (the usual case at the reference's leaf sizes); longer runs - thousands of
+// points per voxel at the coarse multiscale levels of a dense scan - are handed to voxel_long_kernel,
+// because a single thread chasing vals[] -> in[] point by point took 0.6 ms per cloud and level there.
+constexpr int kShortRun = 32;
+
 __global__ void voxel_centroid_kernel(const float4 *__restrict__ in, const unsigned *__restrict__ keys,
                                       const unsigned *__restrict__ vals, const int *__restrict__ pos, size_t n,
-                                      float4 *out) {
+                                      float4 *out, int *long_count, int *long_list) {
     const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned k = keys[i];
@@ -48,6 +53,10 @@ __global__ void voxel_centroid_kernel(const float4 *__restrict__ in, const unsig
     float sx = 0.f, sy = 0.f, sz = 0.f;
     size_t j = i;
     for (; j < n && keys[j] == k; ++j) {
+        if (j - i == (size_t) kShortRun) {   // a long run: a warp takes it from the start
+            long_list[atomicAdd(long_count, 1)] = (int) i;
+            return;
+        }
         const float4 p = in[vals[j]];
         sx = __fadd_rn(sx, p.x);
         sy = __fadd_rn(sy, p.y);
@@ -55,6 +64,56 @@ __global__ void voxel_centroid_kernel(const float4 *__restrict__ in, const unsig
     }
     const float cnt = (float) (j - i);
     out[pos[i]] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 1.0f);
+}
+
+// one warp per long run: the lanes gather 4 x 32 points per trip, the sums stay one sequential chain of fp32
+// adds in run order (lane values handed over by shuffles), so the result is bit-identical to the serial loop
+__global__ void __launch_bounds__(256) voxel_long_kernel(const float4 *__restrict__ in, const unsigned *__restrict__ keys,
+                                                         const unsigned *__restrict__ vals, const int *__restrict__ pos,
+                                                         size_t n, float4 *out, const int *__restrict__ long_count,
+                                                         const int *__restrict__ long_list) {
+    const int total = *long_count;
+    const int lane = threadIdx.x & 31;
+    for (int w = (int) ((blockIdx.x * (size_t) blockDim.x + threadIdx.x) >> 5); w < total;
+         w += (int) ((gridDim.x * (size_t) blockDim.x) >> 5)) {
+        const size_t start = (size_t) long_list[w];
+        const unsigned k = keys[start];
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        size_t count = 0;
+        constexpr int kTrip = 4;
+        bool more = true;
+        for (size_t base = start; more; base += 32 * kTrip) {
+            float4 p[kTrip];
+            unsigned member[kTrip];
+#pragma unroll
+            for (int u = 0; u < kTrip; ++u) {
+                const size_t j = base + (size_t) u * 32 + lane;
+                const bool mine = j < n && keys[j] == k;
+                member[u] = __ballot_sync(0xffffffffu, mine);
+                p[u] = mine ? in[vals[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kTrip; ++u) {
+                const int cnt = __popc(member[u]);   // the run is contiguous: lanes 0 .. cnt-1
+#pragma unroll
+                for (int l = 0; l < 32; ++l) {
+                    const float vx = __shfl_sync(0xffffffffu, p[u].x, l), vy = __shfl_sync(0xffffffffu, p[u].y, l),
+                                vz = __shfl_sync(0xffffffffu, p[u].z, l);
+                    if (l < cnt) {
+                        sx = __fadd_rn(sx, vx);
+                        sy = __fadd_rn(sy, vy);
+                        sz = __fadd_rn(sz, vz);
+                    }
+                }
+                count += (size_t) cnt;
+                if (cnt < 32) more = false;
+            }
+        }
+        if (lane == 0) {
+            const float cnt = (float) count;
+            out[pos[start]] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 1.0f);
+        }
+    }
 }
 
 // pos is the exclusive scan of the head flags: total = pos[n-1] + head(n-1)
@@ -193,14 +252,28 @@ int VoxelWork::filter(const float4 *d_in, size_t n, float leaf, float4 *d_out, s
         if (filtered) *filtered = 0;
         return WAVECU_OK;
     }
-    voxel_centroid_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(d_in, d_keys, d_vals, d_pos, n, d_out);
-    ++launches;
+    // long-run list: worst case one run per kShortRun + 1 points
+    const size_t list_need = n / (kShortRun + 1) + 2;
+    if (list_need > long_cap) {
+        if (d_long) WCU_CHECK(cudaFree(d_long));
+        d_long = nullptr;
+        WCU_CHECK(cudaMalloc((void **) &d_long, (list_need + 64 + 1) * sizeof(int)));
+        long_cap = list_need + 64;
+    }
+    WCU_CHECK(cudaMemsetAsync(d_long, 0, sizeof(int), stream));   // d_long[0] = count, list behind it
+    voxel_centroid_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(d_in, d_keys, d_vals, d_pos, n, d_out, d_long,
+                                                                            d_long + 1);
+    voxel_long_kernel<<<148 * 4, 256, 0, stream>>>(d_in, d_keys, d_vals, d_pos, n, d_out, d_long, d_long + 1);
+    launches += 2;
     WCU_CHECK(cudaGetLastError());
     *n_out = (size_t) n_voxels;
     return WAVECU_OK;
 }
 
 void VoxelWork::release() {
+    if (d_long) cudaFree(d_long);
+    d_long = nullptr;
+    long_cap = 0;
     for (void *p : {(void *) d_keys, (void *) d_keys_alt, (void *) d_vals, (void *) d_vals_alt, (void *) d_pos,
                     (void *) d_bbox, d_tmp})
         if (p) cudaFree(p);

@@ -19,6 +19,8 @@ struct VoxelWork {
     cudaStream_t stream = nullptr;
     unsigned *d_keys = nullptr, *d_keys_alt = nullptr, *d_vals = nullptr, *d_vals_alt = nullptr;
     int *d_pos = nullptr;
+    int *d_long = nullptr;       // [0]: number of long voxel runs, [1..]: their first elements (filter())
+    size_t long_cap = 0;
     unsigned *d_bbox = nullptr;
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0, cap = 0;
