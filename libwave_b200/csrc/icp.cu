@@ -484,10 +484,6 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
     src_sorted_fresh = false;
     src_dirty = false;
     long long extra_launches = 0;
-    if (n_src) {
-        fill_int_kernel<<<(unsigned) ((n_src + 255) / 256), 256, 0, stream>>>(d_nn_pos, -1, n_src);
-        ++extra_launches;
-    }
     SetupArgs sa{src.d_bbox, TG.cloud.d_bbox, d_mc, d_st, d_acc, prm.max_corr, d_fb_count, d_ticket};
     setup_kernel<<<1, 256, 0, stream>>>(sa);
     ++extra_launches;

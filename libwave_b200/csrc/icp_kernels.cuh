@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) correspond_kernel
 
     float best = a.mc->thr;
     int best_idx = 0x7fffffff, best_pos = -1;
-    const int warm = a.nn_pos[s];
+    const int warm = a.st->iter > 0 ? a.nn_pos[s] : -1;   // the first iteration has no previous match
     if (warm >= 0) {
         const float4 p = __ldg(a.tgt + warm);
         const float d = l2_simple(x, y, z, p.x, p.y, p.z);
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) iterate_kernel(co
             moved = make_float4(xform_row(sT + 0, c.x, c.y, c.z), xform_row(sT + 4, c.x, c.y, c.z),
                                 xform_row(sT + 8, c.x, c.y, c.z), c.w);
             a.cur[s] = moved;
-            const int warm = a.nn_pos[s];
+            const int warm = a.st->iter > 0 ? a.nn_pos[s] : -1;   // the first iteration has no previous match
             if (warm >= 0) {
                 const float4 p = __ldg(a.tgt + warm);
                 const float d = l2_simple(moved.x, moved.y, moved.z, p.x, p.y, p.z);

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kTileQ) correspond_tile_kernel(const __grid_co
     int best_slot = -1;   // staged slot of an improvement found in shared memory (converted to a position at the end)
     float r = -1.0f;  // search radius of the warm bound; < 0: no candidate
     if (valid) {
-        const int warm = a.nn_pos[s];
+        const int warm = a.st->iter > 0 ? a.nn_pos[s] : -1;   // the first iteration has no previous match
         if (warm >= 0) {
             const float4 p = __ldg(a.tgt + warm);
             const float d = l2_simple(x, y, z, p.x, p.y, p.z);
