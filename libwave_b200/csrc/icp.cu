@@ -1241,7 +1241,9 @@ int wavecu_icp_correspondences(wavecu_icp *w, int *idx_query, int *idx_match, fl
     WCU_CHECK(cudaSetDevice(h.device));
     const size_t ns = h.result_n_src;
     *n = 0;
-    if (ns == 0 || h.last.iter == 0) return WAVECU_OK;
+    // no search ran (an empty cloud) -> no correspondences; a search that found fewer than three pairs leaves
+    // them in correspondences_ as PCL does (state NO_CORRESPONDENCES, iteration count 0)
+    if (ns == 0 || (h.last.iter == 0 && h.last.state != WAVECU_CONV_NO_CORRESPONDENCES)) return WAVECU_OK;
     fill_int_kernel<<<(unsigned) ((ns + 255) / 256), 256, 0, h.stream>>>(h.d_out_idx, -1, ns);
     unsort_corr_kernel<<<(unsigned) ((ns + 255) / 256), 256, 0, h.stream>>>(h.src.d_sorted, h.d_nn_idx, h.d_nn_d2,
                                                                               (int) ns, h.d_out_idx, h.d_out_d2);
