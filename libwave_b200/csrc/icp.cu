@@ -168,6 +168,7 @@ struct IcpHandle {
     unsigned long long tgt_epoch = 0, tgt_epoch_seen = 0;
     TargetIndex &target() { return tgt_owner ? tgt_owner->tgt : tgt; }
     bool use_tile = false;
+    int refill_rounds = 0, refill_thr = 16;   // lane-refill search (WAVECU_REFILL = queries per lane, 0: off)
     bool use_fused = true;    // one launch per iteration (iterate_kernel); WAVECU_FUSED=0: correspond / reduce / solve
     unsigned *d_ticket = nullptr;
     int *d_fb_count = nullptr, *d_fb_list = nullptr;
@@ -252,6 +253,8 @@ int IcpHandle::init() {
     WCU_CHECK(cudaFuncSetAttribute(correspond_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int) sizeof(TileSmem)));
     if (const char *e = getenv("WAVECU_FUSED")) use_fused = atoi(e) != 0;   // tuning knob
+    if (const char *e = getenv("WAVECU_REFILL")) refill_rounds = std::max(0, std::min(64, atoi(e)));
+    if (const char *e = getenv("WAVECU_REFILL_THR")) refill_thr = atoi(e);
     WCU_CHECK(cudaMalloc((void **) &d_fb_count, sizeof(int)));
     WCU_CHECK(cudaMemset(d_fb_count, 0, sizeof(int)));
     WCU_CHECK(cudaMalloc((void **) &d_ticket, sizeof(unsigned)));
@@ -537,6 +540,11 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             correspond_tile_kernel<<<grid_tile, kTileQ, sizeof(TileSmem), stream>>>(ia, TG.boxes, fb);
             tile_fallback_kernel<<<grid_fb, kIterThreads, 0, stream>>>(ia, fb);
             launches_total += 4;
+        } else if (refill_rounds > 0) {
+            const size_t per_block = (size_t) kIterThreads * refill_rounds;
+            correspond_refill_kernel<<<(unsigned) std::max<size_t>(1, (n_src + per_block - 1) / per_block), kIterThreads, 0, stream>>>(
+                ia, refill_rounds, refill_thr);
+            launches_total += 3;
         } else {
             correspond_kernel<<<grid_nn, kIterThreads, 0, stream>>>(ia);
             launches_total += 3;

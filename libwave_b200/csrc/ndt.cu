@@ -905,10 +905,14 @@ struct NdtHandle {
         derivative_ms = 0;
         bool converged = false;
         int nr_iterations = 0;
+        static const bool trace_steps = getenv("WAVECU_NDT_TRACE") != nullptr;   // debugging aid
         if (grid_dirty || clamped_res() != resolution) {
             const int rc = build_grid();
             if (rc) return rc;
         }
+        // a target without a single cell (no finite point, or VoxelGridCovariance's index overflow, which clears
+        // its output): every derivative is zero, so the first Newton step has norm 0 and PCL reports convergence
+        if (n_src && n_tgt && !grid_ok) converged = true;
         if (n_src && n_tgt && grid_ok) {
             {
                 const int rc = sort_source();
@@ -1005,6 +1009,7 @@ struct NdtHandle {
                     }
                 }
                 delta_p_norm = a_t;
+                if (trace_steps) fprintf(stderr, "[wavecu ndt] iteration %d step %.17g score %.17g\n", nr_iterations, a_t, score);
                 for (int i = 0; i < 6; ++i) p[i] = p[i] + dir[i] * delta_p_norm;
                 if (nr_iterations > prm.max_iter || (nr_iterations && (std::fabs(delta_p_norm) < prm.t_eps)))
                     converged = true;

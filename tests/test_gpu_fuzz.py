@@ -36,3 +36,20 @@ def test_fewer_than_three_pairs_reports_them(oracle):
         q, mm, d2 = m.correspondences()
         assert np.array_equal(q, ref.corr_query) and np.array_equal(mm, ref.corr_match)
         assert np.array_equal(d2, ref.corr_dist)
+
+
+def test_fuzz_gicp_exact():
+    """GICP: both sides add the cost and gradient terms exactly, so flag, outer iterations, evaluation count,
+    correspondence count and the final transform agree bit for bit on every random case."""
+    import fuzz_gicp_ndt
+    assert fuzz_gicp_ndt.run_gicp(21, 50, verbose=True) == 0
+
+
+def test_fuzz_ndt_tolerance():
+    """NDT: flag equal and transform within 1e-4 m / 1e-5 rad with equal iteration counts; the "soft" cases (a step
+    or two more or fewer at the 1e-8 stop threshold, or an oracle path that ran into the iteration cap) are
+    counted, not failed (tools/fuzz_gicp_ndt.py run_ndt)."""
+    import fuzz_gicp_ndt
+    bad, soft = fuzz_gicp_ndt.run_ndt(22, 60, verbose=True)
+    assert bad == 0
+    assert soft <= 6

@@ -10,7 +10,7 @@ fi
 for v in "$@"; do
   name=${v%%:*}; envs=""
   [ "$v" != "$name" ] && envs=$(echo "${v#*:}" | tr ',' ' ')
-  env $envs timeout 600 python bench.py --skip-cpu --steps 10 --warmup 3 > gpurun_out/${tag}_bench_${name}.json 2> gpurun_out/${tag}_bench_${name}.err; echo "bench $name rc=$?"
+  env $envs timeout 600 python bench.py --skip-cpu --no-batch --steps 10 --warmup 3 > gpurun_out/${tag}_bench_${name}.json 2> gpurun_out/${tag}_bench_${name}.err; echo "bench $name rc=$?"
   python - <<PY
 import json
 try:
