@@ -168,7 +168,7 @@ struct IcpHandle {
     unsigned long long tgt_epoch = 0, tgt_epoch_seen = 0;
     TargetIndex &target() { return tgt_owner ? tgt_owner->tgt : tgt; }
     bool use_tile = false;
-    int refill_rounds = 0, refill_thr = 16;   // lane-refill search (WAVECU_REFILL = queries per lane, 0: off)
+    bool tgt_set_since_align = false;   // set_target came before set_source for the coming match
     bool use_fused = true;    // one launch per iteration (iterate_kernel); WAVECU_FUSED=0: correspond / reduce / solve
     unsigned *d_ticket = nullptr;
     int *d_fb_count = nullptr, *d_fb_list = nullptr;
@@ -253,8 +253,6 @@ int IcpHandle::init() {
     WCU_CHECK(cudaFuncSetAttribute(correspond_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int) sizeof(TileSmem)));
     if (const char *e = getenv("WAVECU_FUSED")) use_fused = atoi(e) != 0;   // tuning knob
-    if (const char *e = getenv("WAVECU_REFILL")) refill_rounds = std::max(0, std::min(64, atoi(e)));
-    if (const char *e = getenv("WAVECU_REFILL_THR")) refill_thr = atoi(e);
     WCU_CHECK(cudaMalloc((void **) &d_fb_count, sizeof(int)));
     WCU_CHECK(cudaMemset(d_fb_count, 0, sizeof(int)));
     WCU_CHECK(cudaMalloc((void **) &d_ticket, sizeof(unsigned)));
@@ -323,8 +321,10 @@ int IcpHandle::set_source(const float *xyzw, size_t n, bool from_device) {
     pending_src = nullptr;
     if (!from_device && n) {
         // the caller keeps page-locked buffers untouched until match() returns (wavecu.h): defer
+        // (only while the target of this match has not been given yet: a caller who sets the target first gets
+        // the source copy right behind it, ahead of the normals)
         cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, xyzw) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+        if (!tgt_set_since_align && cudaPointerGetAttributes(&at, xyzw) == cudaSuccess && at.type == cudaMemoryTypeHost) {
             pending_src = xyzw;
             pending_src_n = n;
             return WAVECU_OK;
@@ -363,6 +363,7 @@ int IcpHandle::set_target(const float *xyzw, size_t n, bool from_device) {
     int rc = on_set_target(from_device);
     if (rc) return rc;
     tgt_owner = nullptr;   // a target of its own ends the sharing of another handle's
+    tgt_set_since_align = true;
     rc = tgt.set_points(xyzw, n, from_device);
     if (rc) return rc;
     if (!(prm.res > 0) && n) {  // full resolution: build the search tree behind the copy
@@ -413,6 +414,7 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
         if (rc) return rc;
     }
     have_result = false;
+    tgt_set_since_align = false;
     TargetIndex &TG = target();
     if (tgt_owner) {
         if (TG.dirty) {
@@ -540,11 +542,6 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             correspond_tile_kernel<<<grid_tile, kTileQ, sizeof(TileSmem), stream>>>(ia, TG.boxes, fb);
             tile_fallback_kernel<<<grid_fb, kIterThreads, 0, stream>>>(ia, fb);
             launches_total += 4;
-        } else if (refill_rounds > 0) {
-            const size_t per_block = (size_t) kIterThreads * refill_rounds;
-            correspond_refill_kernel<<<(unsigned) std::max<size_t>(1, (n_src + per_block - 1) / per_block), kIterThreads, 0, stream>>>(
-                ia, refill_rounds, refill_thr);
-            launches_total += 3;
         } else {
             correspond_kernel<<<grid_nn, kIterThreads, 0, stream>>>(ia);
             launches_total += 3;
@@ -637,6 +634,10 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
             fprintf(stderr, "[wavecu timeline ms] src_up %.3f tgt_up %.3f nrm_up %.3f src_sorted %.3f tgt_used %.3f "
                             "align_begin %.3f built %.3f end %.3f\n", at(src.ev_up), at(tgt.cloud.ev_up),
                     at(tgt.ev_nrm_up), at(ev_src_sorted), at(tgt.cloud.ev_used), at(e_begin), at(e_built), at(e_end));
+            if (src.ev_tl[0])
+                fprintf(stderr, "[wavecu timeline ms] src keys %.3f sorted %.3f gathered %.3f | tgt keys %.3f sorted %.3f "
+                                "gathered %.3f\n", at(src.ev_tl[0]), at(src.ev_tl[1]), at(src.ev_tl[2]),
+                        at(tgt.cloud.ev_tl[0]), at(tgt.cloud.ev_tl[1]), at(tgt.cloud.ev_tl[2]));
         }
         first_recorded = false;
         // only iterations that did work count (speculative launches past `done` return at once)

@@ -128,210 +128,6 @@ __global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) correspond_kernel
     a.nn_d2[s] = best;
 }
 
-// ---- search with lane refill ------------------------------------------------------------------------------
-// The walks of the 32 queries of a warp differ in length (ncu: 18-20 of 32 lanes active per instruction with one
-// query per thread), so here a warp owns `rounds` x 32 Morton-consecutive queries and a lane whose walk has ended
-// takes the warp's next query: the walk is a resumable state machine (link / stack / bound per lane), and the warp
-// leaves its stepping loop for the set-up code (transform, warm start, entry-table look-ups) only when at most
-// `thr` lanes are still walking - so the set-up also runs with many lanes.  Same searches, same results as
-// nn_search_cells (same entries, same order of the candidates: every comparison is on the (distance, index) key).
-constexpr int kPhaseIdle = 0, kPhaseOwn = 1, kPhaseFinal = 2, kPhaseSetup2 = 3;
-
-__device__ __forceinline__ void search_chunk(const IterArgs &a, const float *sT, int base, int end, int thr) {
-    const unsigned full = 0xffffffffu;
-    const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
-    const NnIndex &ix = a.ix;
-    const float4 rlo = __ldg(&ix.root->lo), rhi = __ldg(&ix.root->hi);
-    const int root_link = __float_as_int(rlo.w);
-    const bool no_tree = __float_as_int(rhi.w) <= 0 || root_link < 0 || ix.cells == nullptr;  // warp uniform
-    const bool have_prev = a.st->iter > 0;   // the first iteration has no previous match
-    const int shift = ix.key_bits - kCellBits;
-
-    int s = -1, phase = kPhaseIdle, link = kLinkPop, sp = 0, best_pos = -1;
-    float x = 0.f, y = 0.f, z = 0.f;
-    float2 top = make_float2(INFINITY, __int_as_float(kLinkDone));
-    unsigned long long best_key = 0ull;
-    float2 slots[kStackDepth];
-    int next = base;  // warp uniform: the first query not handed out yet
-
-    auto finalize = [&]() {
-        a.nn_pos[s] = best_pos;
-        a.nn_idx[s] = best_pos >= 0 ? (int) (unsigned) best_key : -1;
-        a.nn_d2[s] = key_bound(best_key);
-        phase = kPhaseIdle;
-    };
-    auto enter = [&](int cell) {
-        const int l = __ldg(ix.cells + cell);
-        if (l == kCellEmpty) return;
-        if (l < 0) {  // a single point
-            const float4 p = __ldg(ix.pts + ~l);
-            const unsigned long long k = nn_key(l2_simple(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w));
-            if (k < best_key) {
-                best_key = k;
-                best_pos = ~l;
-            }
-            return;
-        }
-        if (link >= 0) {
-            slots[sp++] = top;
-            top = make_float2(0.0f, __int_as_float(link));  // bound 0: always admitted; its node step prunes
-        }
-        link = l;
-    };
-
-    for (;;) {
-        // ---- set-up: idle lanes take the next queries ----
-        const unsigned idle = __ballot_sync(full, phase == kPhaseIdle);
-        bool fresh = false;
-        if (phase == kPhaseIdle) {
-            const int mine = next + __popc(idle & lt_mask);
-            if (mine < end) {
-                s = mine;
-                fresh = true;
-            }
-        }
-        next = min(end, next + __popc(idle));
-        if (fresh) {
-            const float4 c = a.cur[s];
-            if (!finite3(c.x, c.y, c.z)) {  // pads and non-finite source points take no part
-                a.nn_pos[s] = -1;
-                a.nn_idx[s] = -1;
-                a.nn_d2[s] = INFINITY;
-            } else {
-                x = xform_row(sT + 0, c.x, c.y, c.z);
-                y = xform_row(sT + 4, c.x, c.y, c.z);
-                z = xform_row(sT + 8, c.x, c.y, c.z);
-                a.cur[s] = make_float4(x, y, z, c.w);
-                float best = a.mc->thr;
-                int best_idx = 0x7fffffff;
-                best_pos = -1;
-                const int warm = have_prev ? a.nn_pos[s] : -1;
-                if (warm >= 0) {
-                    const float4 p = __ldg(a.tgt + warm);
-                    const float d = l2_simple(x, y, z, p.x, p.y, p.z);
-                    if (d <= best) {
-                        best = d;
-                        best_idx = __float_as_int(p.w);
-                        best_pos = warm;
-                    }
-                }
-                if (no_tree) {  // empty / single-point target or no entry table: the plain search, on the spot
-                    nn_search(x, y, z, ix, best, best_idx, best_pos);
-                    best_key = nn_key(best, (unsigned) best_idx);
-                    finalize();
-                } else {
-                    best_key = nn_key(best, (unsigned) best_idx);
-                    link = kLinkPop;
-                    top = make_float2(INFINITY, __int_as_float(kLinkDone));
-                    sp = 0;
-                    if (best_pos < 0) {  // no candidate: the own cell first, on its own
-                        const QuantParams qp = make_quant(ix.bbox, ix.key_bits);
-                        const int ox = (int) (quant_axis(x, qp.lx, qp.scale, qp.qmax) >> shift),
-                                  oy = (int) (quant_axis(y, qp.ly, qp.scale, qp.qmax) >> shift),
-                                  oz = (int) (quant_axis(z, qp.lz, qp.scale, qp.qmax) >> shift);
-                        enter(ox | (oy << kCellBits) | (oz << (2 * kCellBits)));
-                        phase = kPhaseOwn;
-                    } else {
-                        phase = kPhaseSetup2;
-                    }
-                }
-            }
-        }
-        if (phase == kPhaseSetup2) {
-            // the cells of the ball around the query (see nn_search_cells); own_done: the query came without a
-            // candidate and its own cell has been searched
-            const bool own_done = sp < 0;
-            sp = 0;
-            link = kLinkPop;
-            top = make_float2(INFINITY, __int_as_float(kLinkDone));
-            const QuantParams qp = make_quant(ix.bbox, ix.key_bits);
-            const int ox = (int) (quant_axis(x, qp.lx, qp.scale, qp.qmax) >> shift),
-                      oy = (int) (quant_axis(y, qp.ly, qp.scale, qp.qmax) >> shift),
-                      oz = (int) (quant_axis(z, qp.lz, qp.scale, qp.qmax) >> shift);
-            const int own = ox | (oy << kCellBits) | (oz << (2 * kCellBits));
-            const float bound = key_bound(best_key);
-            const float r = sqrtf(bound) * 1.00001f + fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) * 1e-6f + 1e-30f;
-            const int ax = (int) (quant_axis(x - r, qp.lx, qp.scale, qp.qmax) >> shift), bx = (int) (quant_axis(x + r, qp.lx, qp.scale, qp.qmax) >> shift);
-            const int ay = (int) (quant_axis(y - r, qp.ly, qp.scale, qp.qmax) >> shift), by = (int) (quant_axis(y + r, qp.ly, qp.scale, qp.qmax) >> shift);
-            const int az = (int) (quant_axis(z - r, qp.lz, qp.scale, qp.qmax) >> shift), bz = (int) (quant_axis(z + r, qp.lz, qp.scale, qp.qmax) >> shift);
-            if (best_pos < 0 || bx - ax > 1 || by - ay > 1 || bz - az > 1) {
-                if (aabb_dist(x, y, z, rlo, rhi) <= bound) link = root_link;
-            } else {
-                for (int cz = az; cz <= bz; ++cz)
-                    for (int cy = ay; cy <= by; ++cy)
-                        for (int cx = ax; cx <= bx; ++cx) {
-                            const int cell = cx | (cy << kCellBits) | (cz << (2 * kCellBits));
-                            if (cell != own) enter(cell);
-                        }
-                if (!own_done) enter(own);  // last = first link to walk
-            }
-            phase = kPhaseFinal;
-        }
-        // ---- walk: one node step / one pop per round and lane ----
-        unsigned run;
-        bool pending = false;
-        for (;;) {
-            if (phase == kPhaseOwn || phase == kPhaseFinal) {
-                if (link >= 0) {
-                    const float4 na = __ldg(&ix.nodes[link].lo0), nb = __ldg(&ix.nodes[link].hi0);
-                    const float4 nc = __ldg(&ix.nodes[link].lo1), nd = __ldg(&ix.nodes[link].hi1);
-                    const int l0 = __float_as_int(na.w), l1 = __float_as_int(nc.w);
-                    const float d0 = aabb_dist(x, y, z, na, nb), d1 = aabb_dist(x, y, z, nc, nd);
-                    const unsigned long long k0 = nn_key(d0, __float_as_uint(nb.w)), k1 = nn_key(d1, __float_as_uint(nd.w));
-                    if (l0 < 0 && k0 < best_key) {
-                        best_key = k0;
-                        best_pos = ~l0;
-                    }
-                    if (l1 < 0 && k1 < best_key) {
-                        best_key = k1;
-                        best_pos = ~l1;
-                    }
-                    const float bound = key_bound(best_key);
-                    const bool in0 = l0 >= 0 && d0 <= bound, in1 = l1 >= 0 && d1 <= bound;
-                    if (in0 && in1) {
-                        const bool right_first = d1 < d0;
-                        slots[sp++] = top;
-                        top = right_first ? make_float2(d0, na.w) : make_float2(d1, nc.w);
-                        link = right_first ? l1 : l0;
-                    } else {
-                        link = in0 ? l0 : (in1 ? l1 : kLinkPop);
-                    }
-                }
-                if (link < 0) {
-                    const int tl = __float_as_int(top.y);
-                    if (tl == kLinkDone) {
-                        if (phase == kPhaseOwn) {
-                            phase = kPhaseSetup2;
-                            sp = -1;  // marks "own cell done" for the set-up
-                        } else {
-                            finalize();
-                        }
-                    } else {
-                        link = (top.x <= key_bound(best_key)) ? tl : kLinkPop;
-                        top = slots[--sp];
-                    }
-                }
-            }
-            run = __ballot_sync(full, phase == kPhaseOwn || phase == kPhaseFinal);
-            if (__popc(run) <= thr) {
-                pending = __any_sync(full, phase == kPhaseSetup2);
-                if (run == 0u || pending || next < end) break;
-            }
-        }
-        if (run == 0u && !pending && next >= end) break;
-    }
-}
-
-__global__ void __launch_bounds__(kIterThreads, WCU_MINBLOCKS) correspond_refill_kernel(IterArgs a, int rounds, int thr) {
-    if (a.st->done) return;
-    __shared__ float sT[12];
-    if (threadIdx.x < 12) sT[threadIdx.x] = a.st->T_inc[threadIdx.x];
-    __syncthreads();
-    const long long base = ((long long) blockIdx.x * (kIterThreads / 32) + (threadIdx.x >> 5)) * 32LL * rounds;
-    if (base >= a.n_src) return;
-    search_chunk(a, sT, (int) base, (int) min((long long) a.n_src, base + 32LL * rounds), thr);
-}
-
 // Estimator reduction over the correspondences (A.4 / 8(a) A7): a streaming pass - 16 B working
 // point + 4 B match position + 4 B distance per source point, 16 B (+16 B normal) gathered per
 // pair - into exact 128-bit fixed-point sums.  One pair per thread; the 16 / 28 terms of a pair

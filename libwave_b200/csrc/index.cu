@@ -440,6 +440,10 @@ int run_captured(GraphCache &cache, cudaStream_t stream, const unsigned long lon
 }  // namespace
 
 int MortonCloud::enqueue_sort(size_t n_sorted_pad, const float4 *d_extra_in, float4 *d_extra_out) {
+    // WAVECU_TIMELINE + WAVECU_NO_GRAPH: events between the phases (not capturable into the cached graph)
+    const bool timeline = getenv("WAVECU_TIMELINE") && !graphs_enabled();
+    if (timeline && !ev_tl[0])
+        for (auto &e : ev_tl) WCU_CHECK(cudaEventCreate(&e));
     bbox_init_kernel<<<1, 32, 0, stream>>>(d_bbox);
     ++launches;
     d_keys_sorted = d_keys;
@@ -450,6 +454,7 @@ int MortonCloud::enqueue_sort(size_t n_sorted_pad, const float4 *d_extra_in, flo
         morton_kernel<<<(unsigned) ((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, stream>>>(
             d_raw, n, d_bbox, key_bits, d_keys, d_vals);
         launches += 2;
+        if (timeline) WCU_CHECK(cudaEventRecord(ev_tl[0], stream));
         cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys_alt);
         cub::DoubleBuffer<unsigned> vb(d_vals, d_vals_alt);
         size_t need = tmp_bytes;
@@ -457,11 +462,13 @@ int MortonCloud::enqueue_sort(size_t n_sorted_pad, const float4 *d_extra_in, flo
         launches += 2 + (3 * key_bits + 8) / 8;  // histogram + scan + onesweep passes (CUB-internal)
         d_keys_sorted = kb.Current();
         d_vals_sorted = vb.Current();
+        if (timeline) WCU_CHECK(cudaEventRecord(ev_tl[1], stream));
     }
     if (n_sorted_pad) {
         gather_kernel<<<(unsigned) ((n_sorted_pad + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, stream>>>(
             d_raw, d_keys_sorted, d_vals_sorted, n, n_sorted_pad, key_bits, d_sorted, d_extra_in, d_extra_out);
         ++launches;
+        if (timeline) WCU_CHECK(cudaEventRecord(ev_tl[2], stream));
     }
     WCU_CHECK(cudaGetLastError());
     return WAVECU_OK;
@@ -499,6 +506,10 @@ void MortonCloud::release() {
     sort_graph.release();
     if (ev_up) cudaEventDestroy(ev_up);
     if (ev_used) cudaEventDestroy(ev_used);
+    for (auto &e : ev_tl) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
     ev_up = ev_used = nullptr;
     up_pending = used_pending = false;
     for (void *p : {(void *) d_raw, (void *) d_sorted, (void *) d_bbox, (void *) d_keys, (void *) d_keys_alt,

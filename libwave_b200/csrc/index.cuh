@@ -60,6 +60,7 @@ struct MortonCloud {
     // copy behind the last sort that read d_raw.  nullptr: everything runs on `stream`.
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_up = nullptr, ev_used = nullptr;
+    cudaEvent_t ev_tl[3] = {nullptr, nullptr, nullptr};   // WAVECU_TIMELINE (debugging aid): keys / sorted / gathered
     bool up_pending = false, used_pending = false;
     size_t n = 0;            // points in d_raw
     size_t cap = 0;          // allocated points
