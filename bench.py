@@ -369,7 +369,7 @@ def run_ours(args):
             assert ok, "match() did not converge on the benchmark workload"
         barrier()
         total_ms_max, pairs_all = batch.reduce_timing(float(sum(ms)), float(pairs), device=dev)
-        return {"total_ms": total_ms_max, "pairs_all": pairs_all, "launches": launches, "iterate_ms": it_ms,
+        return {"total_ms": total_ms_max, "own_ms": float(sum(ms)), "pairs_all": pairs_all, "launches": launches, "iterate_ms": it_ms,
                 "iterate_launches": it_n, "build_ms": build_ms, "solve_ms": solve_ms, "iters": m.iterations}
 
     # `value` and `e2e`: the library as a caller gets it (no per-kernel events).  The per-kernel times behind
@@ -391,6 +391,17 @@ def run_ours(args):
     ok = step_device()
     local = {rank: batch.pack_record(m.getResult(), ok, m.iterations)}
     table = batch.gather_records(local, world, device=dev)
+
+    # what every rank measured on its own pair (the line's times are the max over ranks): [device ms / step,
+    # end-to-end ms / step, ICP iterations]
+    mine = torch.tensor([dev_run["own_ms"] / args.steps, e2e_run["own_ms"] / args.steps, float(dev_run["iters"])],
+                        dtype=torch.float64, device=dev)
+    if world > 1:
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+    else:
+        every = [mine]
+    per_rank = [[round(float(v), 4) for v in t.tolist()] for t in every]
 
     sub = None
     if not args.no_batch:
@@ -447,6 +458,7 @@ def run_ours(args):
                                       "icp_iterations": prof_run["iters"]},
             "results_gathered": {"ranks": int(np.isfinite(table[:, 0]).sum()),
                                  "all_converged": bool(np.nansum(table[:, 16]) == world)},
+            "per_rank_ms_e2e_ms_iterations": per_rank,
             "batch256": sub, "gicp500k": sub_gicp, "ndt1m5m": sub_ndt,
         }
         print(json.dumps(line))

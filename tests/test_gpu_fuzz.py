@@ -53,3 +53,11 @@ def test_fuzz_ndt_tolerance():
     bad, soft = fuzz_gicp_ndt.run_ndt(22, 60, verbose=True)
     assert bad == 0
     assert soft <= 6
+
+
+def test_fuzz_matcher_branches_exact():
+    """ICPMatcher::match() in its three branches (full resolution, voxel grid, multiscale; src/icp.cpp:75-133) plus
+    estimateLUM / estimateLUMold on random scenes: flag, iterations, transform, correspondences, aligned cloud and
+    both information matrices bit-equal to the oracle's."""
+    import fuzz_match
+    assert fuzz_match.run(31, 50, verbose=True) == 0
