@@ -4,19 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload icp1m|batch256|gicp500k|ndt1m5m] [--skip-cpu] [--no-batch]
 
-icp1m (default, the headline; BASELINE.json configs[1]).  One "step" = one ICPMatcher::match()
+icp1m (default, the headline; BASELINE.json configs[1]).  One match = one ICPMatcher::match()
 (point-to-plane estimator, full resolution, reference default parameters) of a 1 M-point synthetic
 Velodyne-style scan against a 1 M-point scan of the same scene (generator: libwave_b200/synth.py,
 SURVEY.md 8(d)), search-structure build included.  Metric: point-pairs/s = sum over ICP iterations of
-source points queried / time.  N > 1: the batch-of-scans case - every rank matches its own scan pair
-(weak scaling), no data-path collective, results gathered once after the timed steps.  The line also
+source points queried / time.  One "step" = one match on each of the MATCHERS_PER_GPU (4) ICPMatcher
+handles of the GPU, all in flight at once, one host thread each - the structure of the reference's
+MultiMatcher (multi_matcher.hpp:32) and of the CPU arm (one match per hardware thread): one pair's
+uploads cross PCIe and its sort / tree build run while the other pairs iterate.  `single_matcher`
+carries the one-match-at-a-time numbers (the `value` / `e2e` of earlier rounds).  N > 1: the
+batch-of-scans case - every rank matches its own scan pairs (weak scaling), no data-path collective,
+results gathered once after the timed steps.  The line also
 carries sub-records: `batch256` (configs[4]: 256 independent 200 k-point scan-to-map alignments sharded
 over the ranks through the C batch API, map indexed once per GPU, one all-gather of the records) and, at N = 1,
 `gicp500k` / `ndt1m5m` (configs[2] / [3], the lines of their own --workload runs with fewer steps).
 
-`value`    inputs already resident in HBM, timed with CUDA events on the launch stream.
-`e2e`      the same match through the public host API from pinned host clouds (H2D copies and the
-           result read-back inside the timed region).
+`value`    inputs already resident in HBM; K steps bracketed by two CUDA events (every match() has
+           returned - result read back - before the second is recorded).
+`e2e`      the same steps through the public host API from pinned host clouds (every match copies its
+           48 MB of inputs to the device and reads its result back inside the timed region).
 `roofline` the dominant kernel (icp1m: iterate_kernel - transform + exact 1-NN + estimator reduction
            in one launch per iteration): algorithmic bytes per launch / mean launch time (CUDA events
            around every launch, inside the timed region) against the measured HBM copy bandwidth in
@@ -50,6 +56,9 @@ CPU_SAMPLE_ITERS = 6          # iterations per CPU sample match (build included)
 METRIC = "point-pairs/s (1M-pt ICP)"
 UNIT = "point-pairs/s"
 L2_FLUSH_BYTES = 256 << 20
+# icp1m: matches in flight per GPU - one ICPMatcher per worker thread, the structure of the reference's MultiMatcher
+# (multi_matcher.hpp:32) and of the CPU arm (one match per hardware thread).  One step = one match per matcher.
+MATCHERS_PER_GPU = max(1, int(os.environ.get("WAVE_BENCH_MATCHERS", "4")))
 
 
 def host_threads() -> int:
@@ -189,9 +198,14 @@ def workload_config(n_gpus: int) -> dict:
                     "same scene, res=-1 (full resolution), max_corr=3, max_iter=100, t_eps=1e-8, fit_eps=1e-2",
         "n_source": N_POINTS, "n_target": N_POINTS, "estimator": "point_to_plane_lls",
         "normals": "analytic surface normals from the generator, uploaded with the target",
-        "parallelism": f"batch-of-scans x{n_gpus} (one independent scan pair per GPU)",
-        "l2": "flushed between timed steps (256 MiB write); inside a step the clouds are re-read every ICP "
-              "iteration by design",
+        "parallelism": f"batch-of-scans: {MATCHERS_PER_GPU} matches in flight per GPU (one ICPMatcher per worker "
+                       f"thread, MultiMatcher's structure, multi_matcher.hpp:32) x {n_gpus} GPU(s); one step = one "
+                       f"match of an independent scan pair per matcher; `single_matcher` holds the one-match-at-a-"
+                       f"time numbers",
+        "matchers_per_gpu": MATCHERS_PER_GPU,
+        "l2": f"inputs larger than L2: a step reads {MATCHERS_PER_GPU} x 48 MB of clouds from the matchers' own "
+              f"buffers and every match streams ~300 MB of its own working set; L2 is flushed (256 MiB write) before "
+              f"the timed region, and between steps for the `single_matcher` numbers",
         "cpu_arm": "one single-threaded oracle match per hardware thread, all at once (MultiMatcher's structure, "
                    "multi_matcher.hpp:32) - conservative against BASELINE.md's 1-thread plan for single-match "
                    "configs; `cores` says how many",
@@ -318,14 +332,73 @@ def run_ours(args):
     src, tgt, nrm = make_workload(rank)
     n = src.shape[0]
     # the matcher launches on this stream, and the timing events below are recorded on it
-    stream = torch.cuda.Stream(device=dev)
-    m = W.ICPMatcher(W.ICPMatcherParams(res=-1, estimator=W.EST_POINT_TO_PLANE), device=local_rank,
-                     stream=stream.cuda_stream)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(MATCHERS_PER_GPU)]
+    crew = [W.ICPMatcher(W.ICPMatcherParams(res=-1, estimator=W.EST_POINT_TO_PLANE), device=local_rank,
+                         stream=st.cuda_stream) for st in streams]
+    stream, m = streams[0], crew[0]
 
-    # device-resident inputs for `value`, pinned host inputs for `e2e`
-    d_src, d_tgt, d_nrm = (torch.from_numpy(a).to(dev) for a in (src, tgt, nrm))
-    h_src, h_tgt, h_nrm = (torch.from_numpy(a).pin_memory() for a in (src, tgt, nrm))
+    # device-resident inputs for `value`, pinned host inputs for `e2e`: every matcher has buffers of its own
+    d_in = [tuple(torch.from_numpy(a).to(dev) for a in (src, tgt, nrm)) for _ in crew]
+    h_in = [tuple(torch.from_numpy(a).pin_memory() for a in (src, tgt, nrm)) for _ in crew]
+    h_np = [tuple(t.numpy() for t in trio) for trio in h_in]
+    d_src, d_tgt, d_nrm = d_in[0]
+    h_src, h_tgt, h_nrm = h_in[0]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def crew_round(mode, count):
+        """Every matcher matches its pair `count` times, all matchers at once (one host thread each)."""
+        fails = []
+
+        def work(i):
+            torch.cuda.set_device(dev)
+            mm = crew[i]
+            for _ in range(count):
+                if mode == "host":
+                    mm.setRef(h_np[i][0])
+                    mm.setTarget(h_np[i][1])
+                    mm.setTargetNormals(h_np[i][2])
+                else:
+                    mm.setRefDevice(d_in[i][0].data_ptr(), n)
+                    mm.setTargetDevice(d_in[i][1].data_ptr(), n)
+                    mm.setTargetNormalsDevice(d_in[i][2].data_ptr(), n)
+                if not mm.match():   # the 4x4 result, flags and trace are read back to the host inside match()
+                    fails.append(i)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(crew))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return fails
+
+    timer = torch.cuda.Stream(device=dev)
+
+    def timed_crew(mode, steps, warmup):
+        """K steps = every matcher does K matches back to back; two events on one stream bracket them (every
+        match() has returned before the second is recorded, so all device work lies between the two)."""
+        crew_round(mode, warmup)
+        barrier()
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(timer)
+        fails = crew_round(mode, steps)
+        e1.record(timer)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        assert not fails, "match() did not converge on the benchmark workload"
+        st = [mm.stats() for mm in crew]
+        pairs = float(sum(x["pairs"] for x in st)) * steps
+        launches = int(sum(x["kernel_launches"] for x in st)) * steps
+        total_ms_max, pairs_all = batch.reduce_timing(float(ms), pairs, device=dev)
+        return {"total_ms": total_ms_max, "own_ms": float(ms), "pairs_all": pairs_all, "launches": launches,
+                "iters": m.iterations}
 
     def step_device():
         m.setRefDevice(d_src.data_ptr(), n)
@@ -338,11 +411,6 @@ def run_ours(args):
         m.setTarget(h_tgt.numpy())
         m.setTargetNormals(h_nrm.numpy())
         return m.match()  # the 4x4 result, flags and trace are read back to the host inside match()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
@@ -378,8 +446,10 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.mark_start()       # clocks are sampled over all three timed passes (each lasts only milliseconds)
-    dev_run = timed(step_device, args.steps, args.warmup)
-    e2e_run = timed(step_host, args.steps, args.warmup)
+    dev_run = timed_crew("device", args.steps, args.warmup)
+    e2e_run = timed_crew("host", args.steps, args.warmup)
+    one_dev = timed(step_device, args.steps, args.warmup)      # one matcher, one match at a time
+    one_e2e = timed(step_host, args.steps, args.warmup)
     m.set_profiling(True)
     prof_run = timed(step_device, args.steps, 1)
     if sampler:
@@ -392,8 +462,8 @@ def run_ours(args):
     local = {rank: batch.pack_record(m.getResult(), ok, m.iterations)}
     table = batch.gather_records(local, world, device=dev)
 
-    # what every rank measured on its own pair (the line's times are the max over ranks): [device ms / step,
-    # end-to-end ms / step, ICP iterations]
+    # what every rank measured on its own pairs (the line's times are the max over ranks): [device ms / step,
+    # end-to-end ms / step, ICP iterations per match]
     mine = torch.tensor([dev_run["own_ms"] / args.steps, e2e_run["own_ms"] / args.steps, float(dev_run["iters"])],
                         dtype=torch.float64, device=dev)
     if world > 1:
@@ -437,8 +507,19 @@ def run_ours(args):
             "ms_per_step": dev_run["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_run["pairs_all"] / (e2e_run["total_ms"] * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(3 * 16 * n), "d2h_bytes_per_step": int(256 + 80 * dev_run["iters"]),
+                    "h2d_bytes_per_step": int(3 * 16 * n) * len(crew) * world,      # whole job, like `value`
+                    "d2h_bytes_per_step": int(256 + 80 * dev_run["iters"]) * len(crew) * world,
+                    "h2d_bytes_per_match": int(3 * 16 * n),
                     "ms_per_step": e2e_run["total_ms"] / args.steps},
+            "matches_per_step": len(crew),
+            "ms_per_match": dev_run["total_ms"] / args.steps / len(crew),
+            "single_matcher": {
+                "what": "one ICPMatcher, one match at a time, L2 flushed between matches (the definition of `value` / "
+                        "`e2e` in earlier rounds); `breakdown_ms_per_step` and `roofline` describe this mode",
+                "value": one_dev["pairs_all"] / (one_dev["total_ms"] * 1e-3),
+                "ms_per_match": one_dev["total_ms"] / args.steps,
+                "e2e_value": one_e2e["pairs_all"] / (one_e2e["total_ms"] * 1e-3),
+                "e2e_ms_per_match": one_e2e["total_ms"] / args.steps},
             "gpu_launches": int(dev_run["launches"]),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "iterate_kernel<point-to-plane> (one launch per ICP iteration: in-place "
