@@ -547,6 +547,44 @@ def run_ours(args):
     return 0
 
 
+def crew_throughput(torch, dev, make_matcher, set_inputs, pairs_of, reps, workers=None):
+    """Throughput of `workers` matchers of one kind taking matches at once on this GPU (one host thread each,
+    device-resident inputs): ms per match and pairs/s, two events on one stream around `reps` matches per matcher."""
+    workers = workers or MATCHERS_PER_GPU
+    streams = [torch.cuda.Stream(device=dev) for _ in range(workers)]
+    crew = [make_matcher(st.cuda_stream) for st in streams]
+    fails = []
+
+    def work(i, count):
+        torch.cuda.set_device(dev)
+        for _ in range(count):
+            set_inputs(crew[i])
+            if not crew[i].match():
+                fails.append(i)
+
+    def round_of(count):
+        th = [threading.Thread(target=work, args=(i, count)) for i in range(workers)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    round_of(1)
+    timer = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(timer)
+    round_of(reps)
+    e1.record(timer)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    pairs = float(sum(pairs_of(mm) for mm in crew)) * reps
+    return {"matchers": workers, "matches_timed": workers * reps, "ms_per_match": ms / (workers * reps),
+            "value": pairs / (ms * 1e-3), "unit": UNIT, "all_converged": not fails,
+            "what": "the same match on several matcher handles at once (MultiMatcher's structure), device-resident "
+                    "inputs; `value` / `e2e` of this record are one matcher, one match at a time"}
+
+
 def finish_dist(dist, world):
     if world > 1:
         dist.barrier()
@@ -733,6 +771,13 @@ def gicp_record(args, W, batch, torch, dist, rank, local_rank, world, dev, steps
     if sampler:
         sampler.mark_end()
     clocks = sampler.finish() if sampler else None
+    crew = None
+    if rank == 0:
+        def feed(mm):
+            mm.setRefDevice(d_src.data_ptr(), n)
+            mm.setTargetDevice(d_tgt.data_ptr(), n)
+        crew = crew_throughput(torch, dev, lambda st_: W.GICPMatcher(W.GICPMatcherParams(res=-1), device=local_rank, stream=st_),
+                               feed, lambda mm: mm.stats()["evaluations"] * n, max(1, steps))
     if rank == 0:
         st = m.stats()
         peak, peak_src = peak_hbm()
@@ -769,7 +814,7 @@ def gicp_record(args, W, batch, torch, dist, rank, local_rank, world, dev, steps
                          "traffic": traffic_of("gicp_cost_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "mean_launch_ms": mean_ms, "launches_timed": int(prof["cost_n"])},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
-            "parity": parity}
+            "parity": parity, "several_matchers": crew}
     return None
 
 
@@ -885,6 +930,13 @@ def ndt_record(args, W, batch, torch, dist, rank, local_rank, world, dev, steps,
     if sampler:
         sampler.mark_end()
     clocks = sampler.finish() if sampler else None
+    crew = None
+    if rank == 0:
+        def feed(mm):
+            mm.setRefDevice(d_src.data_ptr(), n)
+            mm.setTargetDevice(d_tgt.data_ptr(), nt)
+        crew = crew_throughput(torch, dev, lambda st_: W.NDTMatcher(W.NDTMatcherParams(res=0.5), device=local_rank, stream=st_),
+                               feed, lambda mm: mm.stats()["derivative_passes"] * n, max(1, steps))
     if rank == 0:
         st = m.stats()
         peak, peak_src = peak_hbm()
@@ -918,7 +970,8 @@ def ndt_record(args, W, batch, torch, dist, rank, local_rank, world, dev, steps,
                          "traffic": traffic_of("ndt_derivative_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "mean_launch_ms": mean_ms, "launches_timed": int(prof["der_n"])},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
-            "parity": parity, "accuracy": {"translation_error_m": dt_true, "rotation_error_rad": dr_true}}
+            "parity": parity, "accuracy": {"translation_error_m": dt_true, "rotation_error_rad": dr_true},
+            "several_matchers": crew}
     return None
 
 
