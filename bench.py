@@ -59,6 +59,10 @@ L2_FLUSH_BYTES = 256 << 20
 # icp1m: matches in flight per GPU - one ICPMatcher per worker thread, the structure of the reference's MultiMatcher
 # (multi_matcher.hpp:32) and of the CPU arm (one match per hardware thread).  One step = one match per matcher.
 MATCHERS_PER_GPU = max(1, int(os.environ.get("WAVE_BENCH_MATCHERS", "4")))
+if "WAVE_BENCH_MATCHERS" not in os.environ:
+    # every matcher's host thread polls its match; never more threads than this rank's share of the cores
+    _share = (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    MATCHERS_PER_GPU = max(1, min(MATCHERS_PER_GPU, _share - 1))
 
 
 def host_threads() -> int:
