@@ -2,9 +2,10 @@
 
 Bars: the voxel-filtered clouds bit-exact; per-point covariances 1e-9 (they go through a 3x3 eigen
 decomposition: compared where the two smallest eigenvalues are separated, and through the
-surface normal they encode); the match itself - a BFGS over fp64 sums whose order differs between
-CPU and GPU - within the north-star tolerance (1e-4 m, 1e-5 rad) and with the reference tests' own
-bound (||T - T_true||_F < 0.1, tests/gicp_tests.cpp:59,79,99)."""
+surface normal they encode); the match itself - a BFGS whose cost and gradient sums are exact on both
+sides - follows the oracle step for step (same iterations, evaluations, correspondences; transform bit-equal
+on the synthetic scans, within 1e-4 m / 1e-5 rad on the voxel-filtered fixture) and meets the reference tests'
+own bound (||T - T_true||_F < 0.1, tests/gicp_tests.cpp:59,79,99)."""
 import numpy as np
 import pytest
 
