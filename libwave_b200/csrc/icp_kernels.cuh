@@ -18,7 +18,11 @@
 namespace wavecu {
 
 #ifndef WCU_MINBLOCKS
-#define WCU_MINBLOCKS 10   // 40 registers: measured best for the entry-table walk (8: 46 registers, +2 %)
+// 12 blocks of 128 threads = 48 warps per SM at 40 registers (12 B of spills in the fused kernel).  Measured on the
+// 1 M / 1 M match (ms per match, four matchers in flight / one at a time; 200 k batch scans/s): 8: 1.026 / - ; 10 (48
+// registers): 0.958 / 1.222 / 3702; 12: 0.921 / 1.189 / 3802; 16 (32 registers, 76 B spills, and solve_block
+// squeezed into 32 as well): 0.909 / 1.202 / 3172.
+#define WCU_MINBLOCKS 12
 #endif
 #ifndef WCU_ITER_THREADS
 #define WCU_ITER_THREADS 128
