@@ -15,6 +15,7 @@
 //                       cubic and quadratic interpolation), <= 20 inner iterations per outer one, and
 //                       GICP's delta test (entries of the fp32 transform scaled by 1/rotation_epsilon
 //                       or 1/transformation_epsilon).
+#include <sched.h>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -518,6 +519,7 @@ struct GicpHandle {
 #if defined(__x86_64__)
             __builtin_ia32_pause();
 #endif
+            if (spins > 2048 && (spins & 255) == 255) sched_yield();   // see icp.cu: fewer cores than matcher threads
         }
         if (profiling) {
             float ms = 0;

@@ -2,6 +2,7 @@
 // per-align() launch sequence and the C ABI.  Reference behaviour restated: pcl::Registration::
 // align + IterativeClosestPoint::computeTransformation as driven by wave_matching/src/icp.cpp
 // :47-50 (parameters) and :75-133 (ICPMatcher::match).
+#include <sched.h>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -587,6 +588,9 @@ int IcpHandle::align(double *T_out, int *converged, int *iterations, int *state)
 #if defined(__x86_64__)
                 __builtin_ia32_pause();
 #endif
+                // a thread that has been waiting for a while (~0.1 ms) gives its core away now and then: boxes with fewer
+                // cores than matcher threads (8 ranks x several matchers on 32 cores); with a free core it returns at once
+                if (spins > 2048 && (spins & 255) == 255) sched_yield();
             }
             if (v & 1) finished = true;
         }

@@ -15,6 +15,7 @@
 //                combined in a fixed order by a second kernel (deterministic).
 //   host         Newton step through a 6x6 SVD solve and PCL's computeStepLengthMT, including its
 //                PCL 1.8 behaviour that the More-Thuente loop is skipped whenever step_max > step_min.
+#include <sched.h>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -877,6 +878,7 @@ struct NdtHandle {
 #if defined(__x86_64__)
             __builtin_ia32_pause();
 #endif
+            if (spins > 2048 && (spins & 255) == 255) sched_yield();   // see icp.cu: fewer cores than matcher threads
         }
         if (profiling) {
             float ms = 0;
