@@ -32,3 +32,23 @@ for res in (0.5, 0.02):   # dense table / hash table
     n = W.NDTMatcher(W.NDTMatcherParams(res=res))
     n.setup(src, tgt)
     print("ndt", res, n.match(), n.iterations, n.stats()["n_cells"])
+
+# four matchers in flight on one device, one host thread each (bench.py's structure), host and device inputs
+import threading
+import torch
+xs, xt, xn = (synth.to_xyzw(a) for a in (src, tgt, nrm))
+hp = [tuple(torch.from_numpy(a).pin_memory() for a in (xs, xt, xn)) for _ in range(4)]
+crew = [W.ICPMatcher(W.ICPMatcherParams(res=-1, estimator=W.EST_POINT_TO_PLANE)) for _ in range(4)]
+out = []
+
+
+def work(i):
+    mm = crew[i]
+    for _ in range(3):
+        mm.setRef(hp[i][0].numpy()); mm.setTarget(hp[i][1].numpy()); mm.setTargetNormals(hp[i][2].numpy())
+        out.append((i, mm.match(), mm.iterations))
+
+
+th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+[t.start() for t in th]; [t.join() for t in th]
+print("crew", sorted(out))
