@@ -533,7 +533,9 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
                          "search_only_algorithmic_bytes": 40.0 * n,
                          "launches_timed": int(prof_run["iterate_launches"]),
-                         "timed_in": "second pass of the same K steps with per-kernel CUDA events on the launch stream"},
+                         "timed_in": "a further pass of K matches on ONE matcher with per-kernel CUDA events on its launch "
+                                     "stream (with four matchers in flight the launches of different matches overlap and a "
+                                     "per-launch duration stops meaning anything)"},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
             "parity": parity,
             "breakdown_ms_per_step": {"build": prof_run["build_ms"] / args.steps,
