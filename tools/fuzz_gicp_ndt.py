@@ -111,7 +111,9 @@ def run_ndt(seed, n_cases, verbose=True):
         #  * the two grids differ in a cell whose covariance is numerically singular (e.g. seven collinear points):
         #    VoxelGridCovariance drops a cell when its smallest eigenvalue comes out < 0, and for such a matrix that
         #    is +-1e-18 rounding noise - in PCL's own Eigen solver as much as in the two Jacobi iterations here.
-        capped = ref.iterations > kw["max_iter"]
+        #  * fewer than four cells: six degrees of freedom hang on one to three Gaussians, the Hessian is (nearly)
+        #    singular and a long trajectory amplifies the last bits of exp() and of the sums.
+        capped = ref.iterations > kw["max_iter"] or (ref.n_voxels < 4 and ref.iterations >= 10)
         cells_gpu = m.grid()[0]
         cells_ref = O.ndt_grid(tgt, max(kw["res"], 0.05))[0]
         odd = np.setxor1d(cells_gpu, cells_ref)
