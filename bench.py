@@ -8,7 +8,7 @@ icp1m (default, the headline; BASELINE.json configs[1]).  One match = one ICPMat
 (point-to-plane estimator, full resolution, reference default parameters) of a 1 M-point synthetic
 Velodyne-style scan against a 1 M-point scan of the same scene (generator: libwave_b200/synth.py,
 SURVEY.md 8(d)), search-structure build included.  Metric: point-pairs/s = sum over ICP iterations of
-source points queried / time.  One "step" = one match on each of the MATCHERS_PER_GPU (4) ICPMatcher
+source points queried / time.  One "step" = one match on each of the MATCHERS_PER_GPU (6) ICPMatcher
 handles of the GPU, all in flight at once, one host thread each - the structure of the reference's
 MultiMatcher (multi_matcher.hpp:32) and of the CPU arm (one match per hardware thread): one pair's
 uploads cross PCIe and its sort / tree build run while the other pairs iterate.  `single_matcher`
@@ -58,7 +58,8 @@ UNIT = "point-pairs/s"
 L2_FLUSH_BYTES = 256 << 20
 # icp1m: matches in flight per GPU - one ICPMatcher per worker thread, the structure of the reference's MultiMatcher
 # (multi_matcher.hpp:32) and of the CPU arm (one match per hardware thread).  One step = one match per matcher.
-MATCHERS_PER_GPU = max(1, int(os.environ.get("WAVE_BENCH_MATCHERS", "4")))
+# Measured (ms per match resident / end to end): 1 matcher 1.18 / 1.62, 4: 0.911 / 0.947, 6: 0.907 / 0.929, 8: 0.910 / 0.925.
+MATCHERS_PER_GPU = max(1, int(os.environ.get("WAVE_BENCH_MATCHERS", "6")))
 if "WAVE_BENCH_MATCHERS" not in os.environ:
     # every matcher's host thread polls its match; never more threads than this rank's share of the cores
     _share = (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
@@ -534,7 +535,7 @@ def run_ours(args):
                          "search_only_algorithmic_bytes": 40.0 * n,
                          "launches_timed": int(prof_run["iterate_launches"]),
                          "timed_in": "a further pass of K matches on ONE matcher with per-kernel CUDA events on its launch "
-                                     "stream (with four matchers in flight the launches of different matches overlap and a "
+                                     "stream (with several matchers in flight the launches of different matches overlap and a "
                                      "per-launch duration stops meaning anything)"},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
             "parity": parity,
@@ -783,7 +784,7 @@ def gicp_record(args, W, batch, torch, dist, rank, local_rank, world, dev, steps
             mm.setRefDevice(d_src.data_ptr(), n)
             mm.setTargetDevice(d_tgt.data_ptr(), n)
         crew = crew_throughput(torch, dev, lambda st_: W.GICPMatcher(W.GICPMatcherParams(res=-1), device=local_rank, stream=st_),
-                               feed, lambda mm: mm.stats()["evaluations"] * n, max(1, steps))
+                               feed, lambda mm: mm.stats()["evaluations"] * n, max(1, steps), workers=min(4, MATCHERS_PER_GPU))
     if rank == 0:
         st = m.stats()
         peak, peak_src = peak_hbm()
@@ -942,7 +943,7 @@ def ndt_record(args, W, batch, torch, dist, rank, local_rank, world, dev, steps,
             mm.setRefDevice(d_src.data_ptr(), n)
             mm.setTargetDevice(d_tgt.data_ptr(), nt)
         crew = crew_throughput(torch, dev, lambda st_: W.NDTMatcher(W.NDTMatcherParams(res=0.5), device=local_rank, stream=st_),
-                               feed, lambda mm: mm.stats()["derivative_passes"] * n, max(1, steps))
+                               feed, lambda mm: mm.stats()["derivative_passes"] * n, max(1, steps), workers=min(4, MATCHERS_PER_GPU))
     if rank == 0:
         st = m.stats()
         peak, peak_src = peak_hbm()
