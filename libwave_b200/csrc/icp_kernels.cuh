@@ -4,13 +4,17 @@
 //   correspond_kernel  per source point: the in-place incremental fp32 transform of the working
 //                   cloud (A.3.2) fused with the exact 1-NN correspondence search and max-distance
 //                   test (A.3.1).  Kept lean in registers (no accumulators live across the tree
-//                   walk) so that 8+ CTAs stay resident per SM - the walk is latency bound.
+//                   walk) so that 12 CTAs of 128 threads stay resident per SM - the walk is latency bound.
 //   reduce_kernel   streaming pass over the correspondences: {n, sum p, sum q, sum q p^T, sum d2}
 //                   for the SVD estimator (A.4) or the 21+6 entries of J^T J / J^T r for
 //                   point-to-plane (8(a) A7) - as exact 128-bit fixed-point sums (DESIGN.md
 //                   "Estimator arithmetic"): warp butterfly -> block -> a few 64-bit atomics.
 //   solve_kernel    one thread: sums -> Umeyama rotation (one-sided Jacobi, fp64, fixed order) or
 //                   6x6 solve, fp32 cast, final = T * final, DefaultConvergenceCriteria (A.5).
+//   iterate_kernel  the default: the three of them in ONE launch per ICP iteration - every block reduces the
+//                   pairs its own search just found, the last block to finish (a ticket) runs the solve.
+//                   The separate kernels remain for the first iteration while the caller's normals are still
+//                   being uploaded, for the tiled search (tile_nn.cuh) and for A/B runs (WAVECU_FUSED=0).
 #pragma once
 #include "common.cuh"
 #include "index.cuh"
