@@ -25,3 +25,20 @@ def test_reference_arm_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["value"] > 1e6   # a kd-tree ICP on any recent core does millions of point pairs per second
+
+
+def test_matchers_per_gpu_respects_the_cores():
+    """bench.py runs several matchers per GPU, one polling host thread each: never more than this rank's share of
+    the host cores minus one (8 ranks on a 32-core box get three), and the environment override wins."""
+    import os
+    code = "import bench; print(bench.MATCHERS_PER_GPU)"
+    env = {k: v for k, v in os.environ.items() if k not in ("WAVE_BENCH_MATCHERS", "LOCAL_WORLD_SIZE", "WORLD_SIZE")}
+    cores = os.cpu_count() or 1
+    one = int(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env).stdout)
+    assert one == max(1, min(6, cores - 1))
+    many = int(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT,
+                              env={**env, "LOCAL_WORLD_SIZE": "8"}).stdout)
+    assert many == max(1, min(6, cores // 8 - 1))
+    forced = int(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT,
+                                env={**env, "WAVE_BENCH_MATCHERS": "2", "LOCAL_WORLD_SIZE": "8"}).stdout)
+    assert forced == 2
